@@ -1,0 +1,184 @@
+/*
+ * stringwars_b200.h — C ABI of the B200-native batched edit-distance engine.
+ *
+ * This is the drop-in boundary for ONE path of ashvardanian/StringWars: the batched similarity engines
+ * that `similarities/bench.rs` times. Each entry point names the reference interface it replaces
+ * (file:line relative to the StringWars checkout). The reference reaches its engines through the
+ * `stringzilla::szs` Rust types; a Rust (or ctypes / cgo) binding over THIS header gives the same shape —
+ * see INTEGRATION.md for the binding a StringWars maintainer would add.
+ *
+ * Conventions
+ *  - Plain C: opaque handles, raw pointers and sizes; no C++/torch types cross this boundary.
+ *  - Every fallible call returns `swb_status_t` (0 = OK) and, when `err` is non-NULL, stores a pointer to a
+ *    thread-local, NUL-terminated message valid until the next call on the same thread. Nothing aborts or
+ *    throws across the boundary (reference behaviour: `Result<_, E: Display>`, bench.rs:390-399, 599-603).
+ *  - Strings arrive as "tapes": one contiguous byte buffer plus N+1 monotonically increasing u64 offsets
+ *    (Arrow LargeBinary layout == `BytesTapeView<u64>`, bench.rs:62, 292-306). Tapes are read-only.
+ *  - The caller owns inputs and the preallocated result buffer (bench.rs:130, 466-468); the library never
+ *    frees caller memory and performs no allocation in the steady state of a repeated call.
+ *  - Host-pointer calls are blocking: results are host-visible on return (bench.rs:145 `black_box(&matrix)`).
+ *  - One in-flight call per engine handle; handles are not thread-safe (the harness is single-threaded).
+ *  - There is NO CPU fallback. Without a CUDA device `swb_scope_create` fails with SWB_NO_DEVICE.
+ */
+#ifndef STRINGWARS_B200_H_
+#define STRINGWARS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SWB_API
+#else
+#define SWB_API __attribute__((visibility("default")))
+#endif
+
+typedef enum swb_status_t {
+    SWB_OK = 0,
+    SWB_BAD_ALLOC = 1,     /* host or device allocation failed */
+    SWB_INVALID_ARG = 2,   /* NULL pointer, non-monotonic offsets, unsupported cost model, ... */
+    SWB_NO_DEVICE = 3,     /* no usable CUDA device / device ordinal out of range */
+    SWB_CUDA_ERROR = 4,    /* a CUDA runtime call or kernel failed; message carries cudaGetErrorString */
+    SWB_TOO_LONG = 5,      /* an input string exceeds what the selected kernel supports */
+    SWB_UNSUPPORTED = 6    /* feature not built into this library */
+} swb_status_t;
+
+/* Kernel family selection, see DESIGN.md. AUTO picks the fastest exact kernel for the cost model. */
+typedef enum swb_algorithm_t {
+    SWB_ALGO_AUTO = 0,
+    SWB_ALGO_WAVEFRONT = 1, /* anti-diagonal integer DP, sub-warp group per pair, min passed by warp shuffle */
+    SWB_ALGO_BITPARALLEL = 2 /* Myers/Hyyrö bit-vector recurrence (unit costs only), nibble tables in smem */
+} swb_algorithm_t;
+
+/* What a length-k gap costs in the NW/SW engines (the reference's two contenders disagree). */
+typedef enum swb_gap_convention_t {
+    SWB_GAP_STRINGZILLA = 0, /* open + (k-1)*extend — `NeedlemanWunschScores::new(.., open, extend)`, bench.rs:658 */
+    SWB_GAP_BIO = 1          /* open + k*extend     — `Aligner::with_capacity(.., open, extend, ..)`, bench.rs:746 */
+} swb_gap_convention_t;
+
+typedef struct swb_scope swb_scope_t;   /* replaces `szs::DeviceScope`            (bench.rs:376-379) */
+typedef struct swb_engine swb_engine_t; /* replaces the `szs::*Distances/*Scores` engines (bench.rs:382-399, 658-674) */
+
+/* ---- library / device queries ------------------------------------------------------------------------- */
+
+/* Library version, 10000*major + 100*minor + patch. */
+SWB_API int swb_version(void);
+
+/* Number of visible CUDA devices (0 when there is no driver / device). */
+SWB_API int swb_device_count(void);
+
+/* Streaming-multiprocessor count of `device`; replaces `gpu_multiprocessor_count` (utils.rs:826-836), which
+ * the harness uses to size the GPU batch (bench.rs:286-289). */
+SWB_API swb_status_t swb_multiprocessor_count(int device, int *out, const char **err);
+
+/* Total kernels this library has launched in this process (bench.py's `gpu_launches` evidence). */
+SWB_API uint64_t swb_launch_count(void);
+
+/* ---- scopes -------------------------------------------------------------------------------------------- */
+
+/* `DeviceScope::gpu_device(0)` (bench.rs:379). `num_devices` > 1 makes every host-pointer call shard its
+ * batch over devices [first_device, first_device + num_devices) by contiguous pair ranges balanced on cells. */
+SWB_API swb_status_t swb_scope_create(int first_device, int num_devices, swb_scope_t **out, const char **err);
+SWB_API void swb_scope_destroy(swb_scope_t *scope);
+SWB_API int swb_scope_num_devices(const swb_scope_t *scope);
+
+/* ---- pinned host memory ("UnifiedAlloc" replacement) ----------------------------------------------------
+ * The reference keeps its tape in CUDA managed memory (`BytesTape<u64, UnifiedAlloc>`, bench.rs:292). The
+ * B200-native equivalent is page-locked host memory + explicit async copies; tapes and result buffers
+ * allocated here make the host-pointer calls copy at full PCIe rate. Ordinary malloc'd memory also works. */
+SWB_API swb_status_t swb_host_alloc(size_t bytes, void **out, const char **err);
+SWB_API void swb_host_free(void *ptr);
+
+/* ---- engines ------------------------------------------------------------------------------------------- */
+
+/* `LevenshteinDistances::new(&scope, match, mismatch, open, extend)` (bench.rs:382-393). Only the cost model
+ * the harness uses, (0, 1, 1, 1), is accepted; anything else returns SWB_INVALID_ARG. Byte-level symbols. */
+SWB_API swb_status_t swb_levenshtein_create(swb_scope_t *scope, int match, int mismatch, int open, int extend,
+                                            swb_engine_t **out, const char **err);
+
+/* `LevenshteinDistancesUtf8::new(&scope, 0, 1, 1, 1)` (bench.rs:386-399): symbols are Unicode scalar values of
+ * valid UTF-8 input (`rapidfuzz ... distance(a.chars(), b.chars())`, bench.rs:437). */
+SWB_API swb_status_t swb_levenshtein_utf8_create(swb_scope_t *scope, int match, int mismatch, int open,
+                                                 int extend, swb_engine_t **out, const char **err);
+
+/* `NeedlemanWunschScores::new(&scope, &byte_to_class, &class_costs, open, extend)` (bench.rs:658-662):
+ * `byte_to_class` has 256 entries < 32, `class_costs` is 32x32 row-major i8 (bench.rs:98-108). */
+SWB_API swb_status_t swb_needleman_wunsch_create(swb_scope_t *scope, const uint8_t *byte_to_class,
+                                                 const int8_t *class_costs, int open, int extend,
+                                                 swb_engine_t **out, const char **err);
+
+/* `SmithWatermanScores::new(..)` (bench.rs:663-666): best local alignment score (>= 0). */
+SWB_API swb_status_t swb_smith_waterman_create(swb_scope_t *scope, const uint8_t *byte_to_class,
+                                               const int8_t *class_costs, int open, int extend,
+                                               swb_engine_t **out, const char **err);
+
+SWB_API void swb_engine_destroy(swb_engine_t *engine);
+
+/* Options (default AUTO / SWB_GAP_STRINGZILLA). */
+SWB_API swb_status_t swb_engine_set_algorithm(swb_engine_t *engine, swb_algorithm_t algorithm, const char **err);
+SWB_API swb_status_t swb_engine_set_gap_convention(swb_engine_t *engine, swb_gap_convention_t convention,
+                                                   const char **err);
+/* Name of the compute kernel the last call dispatched to (static string). */
+SWB_API const char *swb_engine_last_kernel(const swb_engine_t *engine);
+
+/* Kernel timing for roofline reports: while enabled, every compute-kernel launch (not the schedule kernels) is
+ * bracketed by CUDA events on the stream it is launched on. `swb_engine_kernel_time` synchronises those
+ * events, returns the summed device time in milliseconds and the number of launches since the last call, and
+ * clears the record. */
+SWB_API swb_status_t swb_engine_set_profiling(swb_engine_t *engine, int enabled, const char **err);
+SWB_API swb_status_t swb_engine_kernel_time(swb_engine_t *engine, double *total_ms, uint64_t *launches,
+                                            const char **err);
+
+/* ---- compute: host tapes ------------------------------------------------------------------------------- */
+
+/* Element-wise pairs: out[i] = score(a[i], b[i]) for i < n_pairs. This is the shape BASELINE.json's configs
+ * use and the batched form of the scalar contender surface `(a:&[u8], b:&[u8]) -> usize` (bench.rs:416-419);
+ * precedent for "one result per row pair" is the cuDF row (bench.py:596-604). Distances are written as u64
+ * (`usize`, bench.rs:130); NW/SW scores as i64 (`isize`, bench.rs:193) — pass the i64 buffer cast to u64*. */
+SWB_API swb_status_t swb_compute_pairs(swb_engine_t *engine, const uint8_t *a_data, const uint64_t *a_offsets,
+                                       const uint8_t *b_data, const uint64_t *b_offsets, size_t n_pairs,
+                                       uint64_t *out, const char **err);
+
+/* Cross product: out[q * row_stride + c] = score(queries[q], candidates[c]) — `engine.compute_into(&scope,
+ * queries_tape, Some(candidates_tape), &mut matrix)` (bench.rs:599-603, 123-148). */
+SWB_API swb_status_t swb_compute_cross(swb_engine_t *engine, const uint8_t *q_data, const uint64_t *q_offsets,
+                                       size_t n_queries, const uint8_t *c_data, const uint64_t *c_offsets,
+                                       size_t n_candidates, uint64_t *out, size_t row_stride, const char **err);
+
+/* Scalar convenience, a batch of one through the same kernels: the literal `(a:&[u8], b:&[u8]) -> usize`
+ * surface of bench.rs:416-419. Launch-latency bound; for tests and API compatibility, not for benchmarking.
+ * Returns UINT64_MAX on failure. */
+SWB_API uint64_t swb_levenshtein_pair(swb_engine_t *engine, const uint8_t *a, size_t a_length, const uint8_t *b,
+                                      size_t b_length, const char **err);
+
+/* ---- compute: device-resident tapes -------------------------------------------------------------------- */
+
+/* Same as swb_compute_pairs but every pointer is device memory on scope device `device_index` and the work
+ * is enqueued on `cuda_stream` (a cudaStream_t; NULL = the legacy default stream) without host
+ * synchronisation, except for one small internal readback when the batch needs length bucketing. Offsets
+ * need not start at 0. This is what multi-process callers (one rank per GPU) and the kernel-only bench use. */
+SWB_API swb_status_t swb_compute_pairs_device(swb_engine_t *engine, int device_index, const uint8_t *a_data,
+                                              const uint64_t *a_offsets, const uint8_t *b_data,
+                                              const uint64_t *b_offsets, size_t n_pairs, uint64_t *out,
+                                              void *cuda_stream, const char **err);
+
+SWB_API swb_status_t swb_compute_cross_device(swb_engine_t *engine, int device_index, const uint8_t *q_data,
+                                              const uint64_t *q_offsets, size_t n_queries, const uint8_t *c_data,
+                                              const uint64_t *c_offsets, size_t n_candidates, uint64_t *out,
+                                              size_t row_stride, void *cuda_stream, const char **err);
+
+/* Pair-load phase only: stages every pair's bytes through shared memory with the same coalesced 16-byte
+ * loads the compute kernels use and writes a byte-sum per pair. Exists so the HBM-read rate of the load
+ * phase can be measured on its own (BASELINE.json: ">= 60% of HBM peak on the pair-load phase"). */
+SWB_API swb_status_t swb_load_phase_device(swb_engine_t *engine, int device_index, const uint8_t *a_data,
+                                           const uint64_t *a_offsets, const uint8_t *b_data,
+                                           const uint64_t *b_offsets, size_t n_pairs, uint64_t *out,
+                                           void *cuda_stream, const char **err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STRINGWARS_B200_H_ */

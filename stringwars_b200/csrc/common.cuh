@@ -1,0 +1,102 @@
+// common.cuh — shared device-side helpers for the stringwars_b200 kernels (sm_100a).
+//
+// Data layout in HBM: a "tape" is one contiguous byte buffer plus N+1 u64 offsets, the
+// Arrow LargeBinary layout of `BytesTapeView<u64>` (StringWars similarities/bench.rs:62, 292-306). Kernels
+// address pairs through a PairSpace so that element-wise pairs (BASELINE.json configs) and the harness's
+// cross-product shape (bench.rs:123-148) share every kernel.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace swb {
+
+struct PairSpace {
+    const uint8_t *a_data;
+    const uint64_t *a_offs;
+    const uint8_t *b_data;
+    const uint64_t *b_offs;
+    uint64_t n_pairs;      // total pairs (n_q * n_c in cross mode)
+    uint64_t n_c;          // 0: element-wise pairs; otherwise candidates per query
+    uint64_t stride;       // cross mode: output row stride (elements)
+    const uint32_t *order; // optional permutation (length-bucketed schedule); nullptr = identity
+    uint64_t *out;         // u64 distances or i64 scores
+};
+
+struct PairView {
+    const uint8_t *a, *b;
+    uint32_t la, lb;
+    uint64_t out_index;
+};
+
+__device__ __forceinline__ PairView pair_at(const PairSpace &ps, uint64_t slot) {
+    uint64_t k = ps.order ? (uint64_t)ps.order[slot] : slot;
+    uint64_t ia = k, ib = k, oi = k;
+    if (ps.n_c) {
+        ia = k / ps.n_c;
+        ib = k - ia * ps.n_c;
+        oi = ia * ps.stride + ib;
+    }
+    PairView v;
+    uint64_t a0 = ps.a_offs[ia], a1 = ps.a_offs[ia + 1];
+    uint64_t b0 = ps.b_offs[ib], b1 = ps.b_offs[ib + 1];
+    v.a = ps.a_data + a0;
+    v.b = ps.b_data + b0;
+    v.la = (uint32_t)(a1 - a0);
+    v.lb = (uint32_t)(b1 - b0);
+    v.out_index = oi;
+    return v;
+}
+
+// Read-only 16-byte / 4-byte / 1-byte global loads (LDG through the non-coherent path).
+__device__ __forceinline__ uint4 ldg16(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+__device__ __forceinline__ uint32_t ldg4(const void *p) { return __ldg(reinterpret_cast<const uint32_t *>(p)); }
+__device__ __forceinline__ uint32_t ldg1(const uint8_t *p) { return __ldg(p); }
+
+// Byte k (0..3, compile-time) of a 32-bit word.
+template <int KB>
+__device__ __forceinline__ uint32_t byte_of(uint32_t w) {
+    return __byte_perm(w, 0, 0x4440 + KB);
+}
+
+// Visit every byte of a string that lives in GLOBAL memory, in order: f(index, byte).
+// Aligned 16-byte pieces (one LDG.128, next piece prefetched) with byte loads for the ragged head and tail.
+template <typename F>
+__device__ __forceinline__ void for_each_byte_global(const uint8_t *s, uint32_t len, F &&f) {
+    uint32_t i = 0;
+    const uint32_t head = min(len, (uint32_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(s) & 15u)) & 15u));
+    for (; i < head; ++i) f(i, ldg1(s + i));
+    if (i + 16 <= len) {
+        uint4 nxt = ldg16(s + i);
+        while (i + 16 <= len) {
+            uint4 cur = nxt;
+            if (i + 32 <= len) nxt = ldg16(s + i + 16);
+            const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                f(i + 4 * q + 0, byte_of<0>(w[q]));
+                f(i + 4 * q + 1, byte_of<1>(w[q]));
+                f(i + 4 * q + 2, byte_of<2>(w[q]));
+                f(i + 4 * q + 3, byte_of<3>(w[q]));
+            }
+            i += 16;
+        }
+    }
+    for (; i < len; ++i) f(i, ldg1(s + i));
+}
+
+// Copy `len` bytes from global `src` into shared `dst` using the lanes of one group (lane_in_group of
+// group_size) with aligned 16-byte loads. `dst` must be 16-byte aligned; the copy preserves the source's
+// misalignment, i.e. byte i of the string lands at dst[(src & 15) + i]. Returns that misalignment.
+// Over-reads up to 15 bytes on both sides of the string inside its own 16-byte pieces (always inside the
+// allocation granule of cudaMalloc, never crossing a 16-byte boundary that holds no string byte).
+__device__ __forceinline__ uint32_t stage_string(uint8_t *dst, const uint8_t *src, uint32_t len, int lane_in_group,
+                                                 int group_size) {
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+    const uint8_t *base = src - mis;
+    const uint32_t pieces = len ? (mis + len + 15u) >> 4 : 0u;
+    for (uint32_t p = lane_in_group; p < pieces; p += group_size)
+        *reinterpret_cast<uint4 *>(dst + 16u * p) = ldg16(base + 16u * p);
+    return mis;
+}
+
+} // namespace swb

@@ -1,0 +1,131 @@
+// schedule.cuh — length classification / bucketing of a pair batch, and the load-phase-only kernel.
+//
+// Mixed-length batches (BASELINE.json configs 1 and 3) would make the lanes of a warp run for max(n) columns
+// with the widest pattern's word count; the schedule kernel keys every pair by (pattern-length class,
+// text-length bin), counts the keys and scatters pair indices into a permutation so that every compute kernel
+// launch sees one length class and neighbouring threads see similar text lengths. Uniform batches (configs 2,
+// 4, 5) are detected from the same counters and keep the identity order (no scatter, no indirection).
+#pragma once
+#include "common.cuh"
+
+namespace swb {
+
+constexpr int SCHED_MCLASSES = 9;  // m <= 32, 64, 128, 256, 512, 1024, 2048, 4096, > 4096
+constexpr int SCHED_NBINS = 64;    // text length in steps of 32 bytes, last bin open-ended
+constexpr int SCHED_KEYS = SCHED_MCLASSES * SCHED_NBINS;
+
+struct ScheduleStats {
+    uint32_t counts[SCHED_KEYS];
+    uint32_t cursor[SCHED_KEYS]; // scatter cursors (exclusive prefix of counts), written by the host-side scan
+    uint32_t max_m[SCHED_MCLASSES];
+    uint32_t max_n[SCHED_MCLASSES];
+    uint32_t min_m, max_m_all, min_n, max_n_all;
+};
+
+__device__ __forceinline__ int mclass_of(uint32_t m) {
+    if (m <= 32u) return 0;
+    const int c = 32 - __clz((int)(m - 1u)) - 5; // 33..64 -> 1, 65..128 -> 2, ...
+    return c > SCHED_MCLASSES - 1 ? SCHED_MCLASSES - 1 : c;
+}
+__device__ __forceinline__ int key_of(uint32_t m, uint32_t n) {
+    uint32_t bin = (n + 31u) >> 5;
+    if (bin > (uint32_t)SCHED_NBINS - 1u) bin = SCHED_NBINS - 1;
+    return mclass_of(m) * SCHED_NBINS + (int)bin;
+}
+
+__global__ void __launch_bounds__(256) schedule_count_kernel(PairSpace ps, ScheduleStats *stats) {
+    __shared__ uint32_t s_counts[SCHED_KEYS];
+    __shared__ uint32_t s_max_m[SCHED_MCLASSES], s_max_n[SCHED_MCLASSES];
+    __shared__ uint32_t s_min_m, s_min_n;
+    for (int i = threadIdx.x; i < SCHED_KEYS; i += blockDim.x) s_counts[i] = 0;
+    if (threadIdx.x < SCHED_MCLASSES) s_max_m[threadIdx.x] = 0, s_max_n[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_min_m = 0xFFFFFFFFu, s_min_n = 0xFFFFFFFFu;
+    __syncthreads();
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < ps.n_pairs; k += (uint64_t)gridDim.x * blockDim.x) {
+        PairSpace id = ps;
+        id.order = nullptr;
+        const PairView pv = pair_at(id, k);
+        const uint32_t m = min(pv.la, pv.lb), n = max(pv.la, pv.lb);
+        const int c = mclass_of(m);
+        atomicAdd(&s_counts[key_of(m, n)], 1u);
+        atomicMax(&s_max_m[c], m);
+        atomicMax(&s_max_n[c], n);
+        atomicMin(&s_min_m, m);
+        atomicMin(&s_min_n, n);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SCHED_KEYS; i += blockDim.x)
+        if (s_counts[i]) atomicAdd(&stats->counts[i], s_counts[i]);
+    if (threadIdx.x < SCHED_MCLASSES) {
+        atomicMax(&stats->max_m[threadIdx.x], s_max_m[threadIdx.x]);
+        atomicMax(&stats->max_n[threadIdx.x], s_max_n[threadIdx.x]);
+    }
+    if (threadIdx.x == 0) {
+        atomicMin(&stats->min_m, s_min_m);
+        atomicMin(&stats->min_n, s_min_n);
+    }
+}
+
+__global__ void __launch_bounds__(256) schedule_scatter_kernel(PairSpace ps, ScheduleStats *stats, uint32_t *order) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < ps.n_pairs; k += (uint64_t)gridDim.x * blockDim.x) {
+        PairSpace id = ps;
+        id.order = nullptr;
+        const PairView pv = pair_at(id, k);
+        const uint32_t m = min(pv.la, pv.lb), n = max(pv.la, pv.lb);
+        const uint32_t pos = atomicAdd(&stats->cursor[key_of(m, n)], 1u);
+        order[pos] = (uint32_t)k;
+    }
+}
+
+// Pair-load phase on its own: a block stages the bytes of LOAD_PAIRS consecutive pairs (both tapes) into
+// shared memory with coalesced, aligned 16-byte loads, then thread p byte-sums pair p out of shared memory.
+// Moves exactly the algorithmic bytes of the compute kernels' load phase (+ offsets in, 8 B/pair out).
+constexpr int LOAD_THREADS = 256;
+constexpr int LOAD_PAIRS = 256;
+
+__device__ __forceinline__ uint32_t masked_sum16(const uint8_t *piece, int lo, int hi) {
+    // sum of bytes [lo, hi) of the 16-byte shared-memory piece
+    const uint4 v = *reinterpret_cast<const uint4 *>(piece);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t acc = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t x = w[q];
+        const int b0 = lo - 4 * q, b1 = hi - 4 * q; // keep bytes [b0, b1) of this word
+        if (b1 <= 0 || b0 >= 4) continue;
+        if (b0 > 0) x &= 0xFFFFFFFFu << (8 * b0);
+        if (b1 < 4) x &= 0xFFFFFFFFu >> (8 * (4 - b1));
+        acc = __dp4a(x, 0x01010101u, acc);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(LOAD_THREADS) load_phase_kernel(PairSpace ps, uint32_t cap_a, uint32_t cap_b) {
+    extern __shared__ __align__(16) uint8_t lsm[];
+    uint8_t *s_a = lsm, *s_b = lsm + cap_a;
+    const uint64_t p0 = (uint64_t)blockIdx.x * LOAD_PAIRS;
+    const uint64_t p1 = min(p0 + (uint64_t)LOAD_PAIRS, ps.n_pairs);
+    const uint64_t a_lo = ps.a_offs[p0], a_hi = ps.a_offs[p1], b_lo = ps.b_offs[p0], b_hi = ps.b_offs[p1];
+    const uint8_t *ga = ps.a_data + a_lo, *gb = ps.b_data + b_lo;
+    const uint32_t mis_a = (uint32_t)(reinterpret_cast<uintptr_t>(ga) & 15u), mis_b = (uint32_t)(reinterpret_cast<uintptr_t>(gb) & 15u);
+    stage_string(s_a, ga, (uint32_t)(a_hi - a_lo), threadIdx.x, LOAD_THREADS);
+    stage_string(s_b, gb, (uint32_t)(b_hi - b_lo), threadIdx.x, LOAD_THREADS);
+    __syncthreads();
+    const uint64_t p = p0 + threadIdx.x;
+    if (p < p1) {
+        uint32_t acc = 0;
+        {
+            const uint32_t s = mis_a + (uint32_t)(ps.a_offs[p] - a_lo), e = mis_a + (uint32_t)(ps.a_offs[p + 1] - a_lo);
+            for (uint32_t q = s >> 4; q < (e + 15u) >> 4; ++q)
+                acc += masked_sum16(s_a + 16u * q, (int)max(s, 16u * q) - (int)(16u * q), (int)min(e, 16u * q + 16u) - (int)(16u * q));
+        }
+        {
+            const uint32_t s = mis_b + (uint32_t)(ps.b_offs[p] - b_lo), e = mis_b + (uint32_t)(ps.b_offs[p + 1] - b_lo);
+            for (uint32_t q = s >> 4; q < (e + 15u) >> 4; ++q)
+                acc += masked_sum16(s_b + 16u * q, (int)max(s, 16u * q) - (int)(16u * q), (int)min(e, 16u * q + 16u) - (int)(16u * q));
+        }
+        ps.out[p] = acc;
+    }
+}
+
+} // namespace swb

@@ -1,0 +1,207 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle — bit-exact.
+
+Sizes here are what the oracle finishes in seconds; BASELINE.json's full sizes are covered by
+tests/test_gpu_fullsize.py through size-independent properties plus sampled oracle checks."""
+import numpy as np
+import pytest
+
+import stringwars_b200 as sw
+from stringwars_b200 import datasets
+from stringwars_b200.tape import BytesTape
+
+pytestmark = pytest.mark.gpu
+
+ALGOS = [sw.ALGO_AUTO, sw.ALGO_WAVEFRONT, sw.ALGO_BITPARALLEL]
+
+
+@pytest.fixture(scope="module")
+def scope():
+    s = sw.DeviceScope.gpu_device(0)
+    yield s
+    s.close()
+
+
+@pytest.fixture(scope="module")
+def lev(scope):
+    return sw.LevenshteinDistances(scope, 0, 1, 1, 1)
+
+
+def _check_pairs(engine, scope, oracle, a, b, algo=sw.ALGO_AUTO):
+    engine.set_algorithm(algo)
+    got = engine.compute_pairs(scope, a, b)
+    want = oracle.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, oracle.RAPIDFUZZ_CLASS, threads=8)
+    bad = np.flatnonzero(got != want)
+    assert bad.size == 0, f"{bad.size} mismatches, first at {bad[:5]}: got {got[bad[:5]]} want {want[bad[:5]]} kernel {engine.last_kernel}"
+    engine.set_algorithm(sw.ALGO_AUTO)
+    return got
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_golden_vectors(scope, lev, golden, algo):
+    lev.set_algorithm(algo)
+    a = BytesTape.from_strings([bytes.fromhex(c["a"]) for c in golden])
+    b = BytesTape.from_strings([bytes.fromhex(c["b"]) for c in golden])
+    got = lev.compute_pairs(scope, a, b)
+    want = np.array([c["bytes"] for c in golden], dtype=np.uint64)
+    assert np.array_equal(got, want), np.flatnonzero(got != want)[:10]
+    lev.set_algorithm(sw.ALGO_AUTO)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_config1_words(scope, lev, oracle, algo):
+    a, b = datasets.words_pairs(1000)
+    _check_pairs(lev, scope, oracle, a, b, algo)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_config2_ascii64(scope, lev, oracle, algo):
+    a, b = datasets.ascii_pairs(50_000, 64)
+    _check_pairs(lev, scope, oracle, a, b, algo)
+    if algo == sw.ALGO_AUTO:
+        assert "bitpar" in lev.last_kernel
+    if algo == sw.ALGO_WAVEFRONT:
+        assert "wavefront" in lev.last_kernel
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_config2_mutated(scope, lev, oracle, algo):
+    a, b = datasets.mutated_pairs(3000, 64, 0.1)
+    _check_pairs(lev, scope, oracle, a, b, algo)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_config3_utf8_lines_bytes(scope, lev, oracle, algo):
+    a, b = datasets.utf8_line_pairs(4000)
+    _check_pairs(lev, scope, oracle, a, b, algo)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_config4_ascii256(scope, lev, oracle, algo):
+    a, b = datasets.ascii_pairs(20_000, 256)
+    _check_pairs(lev, scope, oracle, a, b, algo)
+
+
+@pytest.mark.parametrize("algo", [sw.ALGO_AUTO, sw.ALGO_WAVEFRONT])
+def test_long_strings_row_strips(scope, lev, oracle, algo):
+    a, b = datasets.acgt_pairs(300, 1024)
+    _check_pairs(lev, scope, oracle, a, b, algo)
+    a, b = datasets.ascii_pairs(64, 1500, seed=3)
+    _check_pairs(lev, scope, oracle, a, b, algo)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_edge_cases(scope, lev, oracle, algo):
+    strings_a = [b"", b"", b"a", b"abc", b"a" * 31, b"a" * 32, b"a" * 33, b"b" * 64, b"c" * 65, b"x" * 129, b"q" * 257,
+                 b"kitten", b"\x00\xff\x00", b"same", bytes(range(256)), b"z" * 300]
+    strings_b = [b"", b"abc", b"", b"abc", b"a" * 32, b"a" * 31, b"b" * 33, b"b" * 64, b"c" * 64, b"y" * 130, b"q" * 255,
+                 b"sitting", b"\xff\x00\xff", b"same", bytes(range(255, -1, -1)), b"z" * 10]
+    a, b = BytesTape.from_strings(strings_a), BytesTape.from_strings(strings_b)
+    got = _check_pairs(lev, scope, oracle, a, b, algo)
+    assert got[0] == 0 and got[1] == 3 and got[2] == 1 and got[3] == 0 and got[11] == 3
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_ragged_lengths_and_misalignment(scope, lev, oracle, algo):
+    rng = np.random.default_rng(17)
+    for hi in (20, 70, 140, 300):
+        la, lb = rng.integers(0, hi, size=3000), rng.integers(0, hi, size=3000)
+        alphabet = np.arange(97, 101, dtype=np.uint8)
+        a = datasets._ragged(la, alphabet, rng, False)
+        b = datasets._ragged(lb, alphabet, rng, False)
+        _check_pairs(lev, scope, oracle, a, b, algo)
+
+
+def test_empty_batch_and_single_pair(scope, lev):
+    empty = BytesTape.from_strings([])
+    assert lev.compute_pairs(scope, empty, empty).size == 0
+    assert lev.distance(b"kitten", b"sitting") == 3
+    assert lev.distance(b"", b"") == 0
+    assert lev.distance(b"", b"abc") == 3
+
+
+def test_subview_offsets_need_not_start_at_zero(scope, lev, oracle):
+    a, b = datasets.words_pairs(500)
+    va, vb = a.subview(100, 400), b.subview(100, 400)
+    got = lev.compute_pairs(scope, va, vb)
+    want = oracle.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets)[100:400]
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("algo", [sw.ALGO_AUTO, sw.ALGO_WAVEFRONT])
+def test_cross_product_compute_into(scope, lev, oracle, algo):
+    """`compute` / `compute_into` with disjoint query/candidate halves of one tape (bench.rs:123-148)."""
+    lev.set_algorithm(algo)
+    tape = datasets.words_pairs(400)[0]
+    side = 150
+    q, c = tape.subview(0, side), tape.subview(side, 2 * side)
+    matrix = lev.compute(scope, q, c)
+    want = oracle.levenshtein_cross(q.data, q.offsets, c.data, c.offsets, threads=8)
+    assert np.array_equal(matrix, want)
+    wide = np.full((side, side + 7), 12345, dtype=np.uint64)  # row stride > n_candidates
+    lev.compute_into(scope, q, c, wide)
+    assert np.array_equal(wide[:, :side], want) and (wide[:, side:] == 12345).all()
+    lev.set_algorithm(sw.ALGO_AUTO)
+
+
+def test_pinned_tapes(scope, lev, oracle):
+    a, b = datasets.ascii_pairs(10_000, 64, pinned=True)
+    out = sw.PinnedBuffer(8 * 10_000)
+    got = lev.compute_pairs(scope, a, b, out=out.view(np.uint64))
+    want = oracle.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, threads=8)
+    assert np.array_equal(got, want)
+
+
+def test_unsupported_cost_model_is_an_error(scope):
+    with pytest.raises(sw.Error) as e:
+        sw.LevenshteinDistances(scope, 0, 2, 1, 1)
+    assert e.value.status_name == "INVALID_ARG"
+
+
+# ---------------------------------------------------------------- NW / SW scores
+
+@pytest.mark.parametrize("open_,extend", [(-2, -2), (-5, -1)])
+@pytest.mark.parametrize("conv", [sw.GAP_STRINGZILLA, sw.GAP_BIO])
+@pytest.mark.parametrize("local", [False, True])
+def test_alignment_scores(scope, oracle, open_, extend, conv, local):
+    btc, costs = sw.unary_class_costs(2, -1)
+    cls = sw.SmithWatermanScores if local else sw.NeedlemanWunschScores
+    engine = cls(scope, btc, costs, open_, extend).set_gap_convention(conv)
+    for a, b in (datasets.acgt_pairs(300, 100, seed=2), datasets.words_pairs(600, seed=2), datasets.acgt_pairs(40, 1024, seed=3)):
+        got = engine.compute_pairs(scope, a, b)
+        want = oracle.align_pairs(a.data, a.offsets, b.data, b.offsets, btc, costs, open_, extend, conv, local, threads=8)
+        bad = np.flatnonzero(got != want)
+        assert bad.size == 0, (bad[:5], got[bad[:5]], want[bad[:5]], engine.last_kernel)
+
+
+def test_alignment_general_substitution_table(scope, oracle):
+    rng = np.random.default_rng(4)
+    btc = rng.integers(0, 32, size=256).astype(np.uint8)
+    costs = rng.integers(-6, 7, size=(32, 32)).astype(np.int8)  # asymmetric on purpose
+    a, b = datasets.utf8_line_pairs(300, 20, 200, seed=4)
+    for cls, local in ((sw.NeedlemanWunschScores, False), (sw.SmithWatermanScores, True)):
+        engine = cls(scope, btc, costs, -3, -1)
+        got = engine.compute_pairs(scope, a, b)
+        want = oracle.align_pairs(a.data, a.offsets, b.data, b.offsets, btc, costs, -3, -1, 0, local, threads=8)
+        assert np.array_equal(got, want)
+
+
+def test_alignment_cross(scope, oracle):
+    btc, costs = sw.unary_class_costs(2, -1)
+    engine = sw.NeedlemanWunschScores(scope, btc, costs, -2, -2)
+    tape = datasets.acgt_pairs(120, 90, seed=6)[0]
+    q, c = tape.subview(0, 60), tape.subview(60, 120)
+    got = engine.compute(scope, q, c)
+    want = oracle.align_cross(q.data, q.offsets, c.data, c.offsets, btc, costs, -2, -2, threads=8)
+    assert got.dtype == np.int64 and np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------- multi-device scope (single process)
+
+def test_multi_device_scope_matches_single(scope, lev, oracle):
+    if sw.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    a, b = datasets.ascii_pairs(30_001, 64, seed=8)  # not divisible by the device count
+    single = lev.compute_pairs(scope, a, b)
+    multi_scope = sw.DeviceScope.gpu_devices(0, sw.device_count())
+    multi = sw.LevenshteinDistances(multi_scope).compute_pairs(multi_scope, a, b)
+    assert np.array_equal(single, multi)
