@@ -38,6 +38,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #define ORC_EXPORT __attribute__((visibility("default")))
 
@@ -261,6 +262,7 @@ typedef struct {
     const uint8_t *a_data, *b_data;
     const uint64_t *a_offs, *b_offs;
     size_t lo, hi;   /* pair range (pairs mode) or flat cell range (cross mode) */
+    int repeats;     /* timing runs: walk the range this many times (>= 1) */
     size_t n_c;      /* cross mode: candidates per query; 0 = element-wise pairs */
     size_t stride;   /* cross mode: output row stride in elements */
     int64_t *out;
@@ -271,6 +273,7 @@ typedef struct {
 
 static void *orc_worker(void *arg) {
     orc_job_t *job = (orc_job_t *)arg;
+    for (int rep = 0; rep < (job->repeats > 0 ? job->repeats : 1); ++rep)
     for (size_t k = job->lo; k < job->hi; ++k) {
         size_t ia = job->n_c ? k / job->n_c : k, ib = job->n_c ? k % job->n_c : k;
         const uint8_t *a = job->a_data + job->a_offs[ia];
@@ -347,4 +350,18 @@ ORC_EXPORT void orc_align_cross(const uint8_t *q_data, const uint64_t *q_offs, s
     job.out = out, job.n_c = n_c, job.stride = stride, job.byte_to_class = byte_to_class, job.costs = costs;
     job.open = open, job.extend = extend, job.convention = convention, job.local = local;
     if (n_c) orc_run(job, n_q * n_c, threads);
+}
+
+/* Timed variant for the CPU baseline: every thread walks its share of the batch `repeats` times; returns the
+ * wall seconds between thread creation and the last join (so start-up cost is amortised, not hidden). */
+ORC_EXPORT double orc_lev_pairs_timed(int kind, const uint8_t *a_data, const uint64_t *a_offs, const uint8_t *b_data,
+                                      const uint64_t *b_offs, size_t n_pairs, uint64_t *out, int threads, int repeats) {
+    orc_job_t job = {0};
+    job.kind = kind, job.a_data = a_data, job.a_offs = a_offs, job.b_data = b_data, job.b_offs = b_offs;
+    job.out = (int64_t *)out, job.repeats = repeats;
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    orc_run(job, n_pairs, threads);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }

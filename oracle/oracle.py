@@ -50,6 +50,9 @@ def lib() -> ctypes.CDLL:
                                       _u8p, _i8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.orc_lev_pairs.restype = None
         L.orc_lev_pairs.argtypes = [ctypes.c_int, _u8p, _u64p, _u8p, _u64p, ctypes.c_size_t, _u64p, ctypes.c_int]
+        L.orc_lev_pairs_timed.restype = ctypes.c_double
+        L.orc_lev_pairs_timed.argtypes = [ctypes.c_int, _u8p, _u64p, _u8p, _u64p, ctypes.c_size_t, _u64p, ctypes.c_int,
+                                          ctypes.c_int]
         L.orc_lev_cross.restype = None
         L.orc_lev_cross.argtypes = [ctypes.c_int, _u8p, _u64p, ctypes.c_size_t, _u8p, _u64p, ctypes.c_size_t,
                                     _u64p, ctypes.c_size_t, ctypes.c_int]
@@ -89,6 +92,19 @@ def levenshtein_pairs(a_data, a_offs, b_data, b_offs, kind: int = WAGNER_FISCHER
     lib().orc_lev_pairs(kind, _p(a_data, ctypes.c_uint8), _p(a_offs, ctypes.c_uint64), _p(b_data, ctypes.c_uint8),
                         _p(b_offs, ctypes.c_uint64), n, _p(out, ctypes.c_uint64), threads)
     return out
+
+
+def levenshtein_pairs_timed(a_data, a_offs, b_data, b_offs, kind: int = RAPIDFUZZ_CLASS, threads: int = 1,
+                            repeats: int = 1):
+    """(seconds, results): wall time measured inside C around `threads` workers each doing `repeats` passes."""
+    a_data, a_offs = _tape(a_data, a_offs)
+    b_data, b_offs = _tape(b_data, b_offs)
+    n = len(a_offs) - 1
+    out = np.zeros(n, dtype=np.uint64)
+    secs = lib().orc_lev_pairs_timed(kind, _p(a_data, ctypes.c_uint8), _p(a_offs, ctypes.c_uint64),
+                                     _p(b_data, ctypes.c_uint8), _p(b_offs, ctypes.c_uint64), n,
+                                     _p(out, ctypes.c_uint64), threads, repeats)
+    return float(secs), out
 
 
 def levenshtein_cross(q_data, q_offs, c_data, c_offs, kind: int = WAGNER_FISCHER, threads: int = 1) -> np.ndarray:

@@ -10,6 +10,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <set>
@@ -43,6 +44,17 @@ static swb_status_t fail(const char **err, swb_status_t st, const char *fmt, ...
             return fail(err, e_ == cudaErrorMemoryAllocation ? SWB_BAD_ALLOC : SWB_CUDA_ERROR, "%s failed: %s", \
                         #call, cudaGetErrorString(e_));                                                        \
     } while (0)
+
+// ------------------------------------------------------------------------------------------ tracing
+// SWB_TRACE=1 prints host-side phase timestamps of the host-tape pipeline to stderr (diagnostics only).
+#include <chrono>
+static bool trace_enabled() {
+    static const bool on = getenv("SWB_TRACE") && getenv("SWB_TRACE")[0] == '1';
+    return on;
+}
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 // ------------------------------------------------------------------------------------------ objects
 
@@ -372,12 +384,13 @@ static inline uint32_t round16(uint32_t x) { return (x + 15u) & ~15u; }
 template <int K>
 static swb_status_t launch_bitpar(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count,
                                   cudaStream_t stream, const char **err) {
-    const size_t smem = (size_t)32 * BP_THREADS * K * sizeof(uint32_t);
+    constexpr int T = BitparConfig<K>::THREADS;
+    const size_t smem = (size_t)32 * T * K * sizeof(uint32_t);
     SWB_CUDA(allow_smem((const void *)lev_bitpar_kernel<K>, ctx.device, smem));
-    const uint64_t blocks = (count + BP_THREADS - 1) / BP_THREADS;
+    const uint64_t blocks = (count + T - 1) / T;
     {
         ProfileBracket bracket(eng, ctx.device, stream);
-        lev_bitpar_kernel<K><<<(unsigned)blocks, BP_THREADS, smem, stream>>>(ps, begin, count);
+        lev_bitpar_kernel<K><<<(unsigned)blocks, T, smem, stream>>>(ps, begin, count);
     }
     g_launches++;
     static const char *names[] = {"", "lev_bitpar<K=1>", "lev_bitpar<K=2>", "", "lev_bitpar<K=4>", "", "", "", "lev_bitpar<K=8>"};
@@ -386,19 +399,21 @@ static swb_status_t launch_bitpar(swb_engine *eng, DeviceCtx &ctx, const PairSpa
     return SWB_OK;
 }
 
-template <int G, int R, bool LOCAL, bool AFFINE, typename BoundT>
+template <int G, int R, bool LOCAL, bool AFFINE, bool UNARY, typename BoundT>
 static swb_status_t launch_wavefront_t(swb_engine *eng, DeviceCtx &ctx, int dev_index, const PairSpace &ps, uint64_t begin,
                                        uint64_t count, const AlignCosts &cs, uint32_t max_m, uint32_t max_n,
                                        cudaStream_t stream, const char **err) {
     constexpr int PPB = WF_THREADS / G;
+    constexpr bool SHIFTED = !LOCAL && !AFFINE && UNARY;
+    const bool single_strip = max_m <= (uint32_t)(G * R);
     const uint32_t slot_rows = round16(max_m + 16u) + 16u, slot_cols = round16(max_n + 16u) + 16u;
-    const uint32_t bound_cap = max_n + 1u;
+    const uint32_t bound_cap = (SHIFTED && single_strip) ? 0u : max_n + 1u; // shifted single-strip cells need no boundary row
     const uint32_t bound_bytes = round16(bound_cap * (uint32_t)sizeof(BoundT) * (AFFINE ? 2u : 1u));
     const size_t smem = 2304 + (size_t)PPB * (slot_rows + slot_cols + bound_bytes);
     if (smem > (size_t)ctx.max_smem_optin)
         return fail(err, SWB_TOO_LONG, "pair of %u x %u bytes needs %zu B of shared memory per block (limit %d)", max_m, max_n,
                     smem, ctx.max_smem_optin);
-    auto kernel = align_wavefront_kernel<G, R, LOCAL, AFFINE, BoundT>;
+    auto kernel = align_wavefront_kernel<G, R, LOCAL, AFFINE, UNARY, BoundT>;
     SWB_CUDA(allow_smem((const void *)kernel, ctx.device, smem));
     const uint64_t blocks = (count + PPB - 1) / PPB;
     {
@@ -412,41 +427,50 @@ static swb_status_t launch_wavefront_t(swb_engine *eng, DeviceCtx &ctx, int dev_
 
 template <int G, int R>
 static swb_status_t launch_wavefront_gr(swb_engine *eng, DeviceCtx &ctx, int dev_index, const PairSpace &ps, uint64_t begin,
-                                        uint64_t count, const AlignCosts &cs, bool local, bool affine, bool narrow,
+                                        uint64_t count, const AlignCosts &cs, bool local, bool affine, bool unary, bool narrow,
                                         uint32_t max_m, uint32_t max_n, cudaStream_t stream, const char **err) {
-#define SWB_WF(L, A, T) return launch_wavefront_t<G, R, L, A, T>(eng, ctx, dev_index, ps, begin, count, cs, max_m, max_n, stream, err)
-    if (!local && !affine && narrow) SWB_WF(false, false, int16_t);
-    if (!local && !affine && !narrow) SWB_WF(false, false, int32_t);
-    if (!local && affine && narrow) SWB_WF(false, true, int16_t);
-    if (!local && affine && !narrow) SWB_WF(false, true, int32_t);
-    if (local && !affine && narrow) SWB_WF(true, false, int16_t);
-    if (local && !affine && !narrow) SWB_WF(true, false, int32_t);
-    if (local && affine && narrow) SWB_WF(true, true, int16_t);
-    SWB_WF(true, true, int32_t);
+#define SWB_WF(L, A, U, T) return launch_wavefront_t<G, R, L, A, U, T>(eng, ctx, dev_index, ps, begin, count, cs, max_m, max_n, stream, err)
+    if (!unary) { // general 32x32 substitution table: int32 boundary rows only
+        if (!local && !affine) SWB_WF(false, false, false, int32_t);
+        if (!local && affine) SWB_WF(false, true, false, int32_t);
+        if (local && !affine) SWB_WF(true, false, false, int32_t);
+        SWB_WF(true, true, false, int32_t);
+    }
+    if (!local && !affine && narrow) SWB_WF(false, false, true, int16_t);
+    if (!local && !affine && !narrow) SWB_WF(false, false, true, int32_t);
+    if (!local && affine && narrow) SWB_WF(false, true, true, int16_t);
+    if (!local && affine && !narrow) SWB_WF(false, true, true, int32_t);
+    if (local && !affine && narrow) SWB_WF(true, false, true, int16_t);
+    if (local && !affine && !narrow) SWB_WF(true, false, true, int32_t);
+    if (local && affine && narrow) SWB_WF(true, true, true, int16_t);
+    SWB_WF(true, true, true, int32_t);
 #undef SWB_WF
 }
 
 static swb_status_t launch_wavefront(swb_engine *eng, DeviceCtx &ctx, int dev_index, const PairSpace &ps, uint64_t begin,
                                      uint64_t count, uint32_t max_m, uint32_t max_n, cudaStream_t stream, const char **err) {
     AlignCosts cs;
-    cs.match = eng->match, cs.mismatch = eng->mismatch, cs.unary = eng->unary ? 1 : 0;
-    cs.negate = (eng->kind == ENGINE_LEVENSHTEIN || eng->kind == ENGINE_LEVENSHTEIN_UTF8) ? 1 : 0;
-    cs.first = eng->convention == SWB_GAP_BIO && !cs.negate ? eng->open + eng->extend : eng->open;
+    const bool is_lev = eng->kind == ENGINE_LEVENSHTEIN || eng->kind == ENGINE_LEVENSHTEIN_UTF8;
+    cs.match = eng->match, cs.mismatch = eng->mismatch;
+    cs.ident = is_lev ? 1 : 0;
+    cs.negate = is_lev ? 1 : 0;
+    cs.first = eng->convention == SWB_GAP_BIO && !is_lev ? eng->open + eng->extend : eng->open;
     cs.next = eng->extend;
     const bool local = eng->kind == ENGINE_SW;
     const bool affine = cs.first != cs.next;
-    // int16 boundary rows when every reachable |score| stays far inside the int16 range
+    // int16 boundary rows when every reachable |score| (also in the shifted H - gap*(i+j) form) stays inside int16
     int maxabs = std::max(std::abs(cs.first), std::abs(cs.next));
-    if (cs.unary) maxabs = std::max(maxabs, std::max(std::abs(cs.match), std::abs(cs.mismatch)));
+    if (eng->unary) maxabs = std::max(maxabs, std::max(std::abs(cs.match), std::abs(cs.mismatch)));
     else maxabs = std::max(maxabs, 128);
-    const bool narrow = (uint64_t)(max_m + max_n + 2u) * (uint64_t)maxabs < 30000u;
+    const bool narrow = (uint64_t)(max_m + max_n + 2u) * 3u * (uint64_t)maxabs < 30000u;
 #define SWB_GR(G, R, NAME)                                                                                           \
     do {                                                                                                           \
         eng->last_kernel = NAME;                                                                                   \
-        return launch_wavefront_gr<G, R>(eng, ctx, dev_index, ps, begin, count, cs, local, affine, narrow, max_m, max_n, stream, err); \
+        return launch_wavefront_gr<G, R>(eng, ctx, dev_index, ps, begin, count, cs, local, affine, eng->unary, narrow, max_m, max_n, stream, err); \
     } while (0)
-    if (max_m <= 32) SWB_GR(4, 8, "align_wavefront<G=4,R=8>");
-    if (max_m <= 64) SWB_GR(8, 8, "align_wavefront<G=8,R=8>");
+    if (max_m <= 16) SWB_GR(1, 16, "align_wavefront<G=1,R=16>");
+    if (max_m <= 32) SWB_GR(2, 16, "align_wavefront<G=2,R=16>");
+    if (max_m <= 64) SWB_GR(4, 16, "align_wavefront<G=4,R=16>");
     if (max_m <= 128) SWB_GR(8, 16, "align_wavefront<G=8,R=16>");
     if (max_m <= 256) SWB_GR(16, 16, "align_wavefront<G=16,R=16>");
     SWB_GR(32, 16, "align_wavefront<G=32,R=16>");
@@ -667,6 +691,8 @@ extern "C" swb_status_t swb_compute_pairs(swb_engine_t *engine, const uint8_t *a
     };
     std::vector<Shard> shards(D);
 
+    const double t_begin = trace_enabled() ? now_ms() : 0;
+    double t_phase1 = 0, t_stats = 0, t_phase2 = 0;
     // Phase 1: per device, enqueue offsets H2D, schedule counters, then chunked data H2D.
     for (int d = 0; d < D; ++d) {
         DeviceCtx &ctx = scope->devs[d];
@@ -710,6 +736,7 @@ extern "C" swb_status_t swb_compute_pairs(swb_engine_t *engine, const uint8_t *a
         }
     }
 
+    if (trace_enabled()) t_phase1 = now_ms();
     // Phase 2: per device, read the counters, then launch per chunk (identity) or per class (bucketed).
     for (int d = 0; d < D; ++d) {
         DeviceCtx &ctx = scope->devs[d];
@@ -718,6 +745,7 @@ extern "C" swb_status_t swb_compute_pairs(swb_engine_t *engine, const uint8_t *a
         if (n == 0) continue;
         SWB_CUDA(cudaSetDevice(ctx.device));
         SWB_CUDA(cudaEventSynchronize(ctx.ev_stats));
+        if (trace_enabled() && d == 0) t_stats = now_ms();
         Plan plan = make_plan(*ctx.h_stats);
         const int chunks = (int)sh.chunk_cut.size() - 1;
         if (plan.identity) {
@@ -742,12 +770,16 @@ extern "C" swb_status_t swb_compute_pairs(swb_engine_t *engine, const uint8_t *a
             SWB_CUDA(cudaMemcpyAsync(out + sh.lo, ctx.out.ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx.compute_stream));
         }
     }
+    if (trace_enabled()) t_phase2 = now_ms();
     // Phase 3: results are host-visible on return.
     for (int d = 0; d < D; ++d) {
         if (shards[d].hi == shards[d].lo) continue;
         SWB_CUDA(cudaSetDevice(scope->devs[d].device));
         SWB_CUDA(cudaStreamSynchronize(scope->devs[d].compute_stream));
     }
+    if (trace_enabled())
+        fprintf(stderr, "[swb trace] pairs=%zu enqueue=%.3f ms stats_wait=%.3f ms launch=%.3f ms drain=%.3f ms total=%.3f ms\n", n_pairs,
+                t_phase1 - t_begin, t_stats - t_phase1, t_phase2 - t_stats, now_ms() - t_phase2, now_ms() - t_begin);
     return SWB_OK;
 }
 

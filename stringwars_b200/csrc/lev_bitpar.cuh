@@ -1,7 +1,7 @@
 // lev_bitpar.cuh — unit-cost Levenshtein by the Myers (1999) / Hyyrö (2003) bit-vector recurrence, sm_100a.
 //
 // Why this exists next to the wavefront kernel: with unit costs the vertical/horizontal DP deltas are in
-// {-1, 0, +1}, so 32 DP rows fit two 32-bit masks and one column step costs ~12 LOP3/IADD/SHF per 32 cells
+// {-1, 0, +1}, so 32 DP rows fit two 32-bit masks and one column step costs ~10 LOP3/SHF per 32 cells
 // instead of ~4-5 integer instructions per cell. Integer ALU issue is the binding roofline of this path
 // (DESIGN.md §5), so this is the kernel that moves the HBM-roofline fraction.
 //
@@ -13,6 +13,16 @@
 // aligned 16-byte read-only loads, one piece prefetched (thread-private strings: nothing to share, so no
 // smem staging here — the group-per-pair wavefront kernel is the one that stages).
 //
+// Instruction-level design (the kernel is ALU-pipe bound, ncu: profiles/r1_*):
+//  * The pattern is TOP-aligned: symbol i sits at bit s+i, s = 32K-m. The s rows below it are "free" rows
+//    (vertical delta 0, never matching) that replicate DP row 0, so the result is unchanged while the last
+//    pattern row is always bit 31 of word K-1: the score update is two shifts, no runtime bit index, no
+//    per-word predication.
+//  * `x << 1 | carry` is written as x*2+carry and the adds as mul-adds: they issue on the FMA pipe (IMAD),
+//    which is otherwise idle, instead of the saturated ALU pipe.
+//  * Symbols are nibble-split four at a time ((w >> 4) & 0x0F0F0F0F, w & 0x0F0F0F0F); a table address is one
+//    byte extract plus one IMAD.
+//
 // Parity: bit-exact with the CPU oracle (both of its algorithm families), the restatement of
 // `rapidfuzz::distance::levenshtein::distance` as called at StringWars similarities/bench.rs:416-419.
 #pragma once
@@ -20,53 +30,43 @@
 
 namespace swb {
 
-constexpr int BP_THREADS = 128;
-
 template <int K>
-struct WordVec;
-template <>
-struct WordVec<1> {
-    using type = uint32_t;
-};
-template <>
-struct WordVec<2> {
-    using type = uint2;
-};
-template <>
-struct WordVec<4> {
-    using type = uint4;
+struct BitparConfig {
+    static constexpr int THREADS = K <= 4 ? 128 : 64; // 128 * K bytes of tables per thread
 };
 
-// Load the K table words of entry `e` for this thread.
+// K table words of the entry at `p` (shared memory).
 template <int K>
-__device__ __forceinline__ void load_entry(const uint32_t *tbl, int e, int tid, uint32_t (&w)[K]) {
-    const uint32_t *p = tbl + ((size_t)e * BP_THREADS + tid) * K;
+__device__ __forceinline__ void load_words(const unsigned char *p, uint32_t (&w)[K]) {
     if constexpr (K == 1) {
-        w[0] = p[0];
+        w[0] = *reinterpret_cast<const uint32_t *>(p);
     } else if constexpr (K == 2) {
-        uint2 v = *reinterpret_cast<const uint2 *>(p);
+        const uint2 v = *reinterpret_cast<const uint2 *>(p);
         w[0] = v.x, w[1] = v.y;
     } else {
 #pragma unroll
         for (int q = 0; q < K / 4; ++q) {
-            uint4 v = *reinterpret_cast<const uint4 *>(p + 4 * q);
+            const uint4 v = *reinterpret_cast<const uint4 *>(p + 16 * q);
             w[4 * q + 0] = v.x, w[4 * q + 1] = v.y, w[4 * q + 2] = v.z, w[4 * q + 3] = v.w;
         }
     }
 }
 
 template <int K>
-__global__ void __launch_bounds__(BP_THREADS) lev_bitpar_kernel(PairSpace ps, uint64_t begin, uint64_t count) {
-    extern __shared__ __align__(16) uint32_t tbl[]; // [32 entries][BP_THREADS][K]
+__global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(PairSpace ps, uint64_t begin, uint64_t count) {
+    constexpr int T = BitparConfig<K>::THREADS;
+    constexpr uint32_t ESTRIDE = T * K * 4; // bytes between consecutive table entries
+    extern __shared__ __align__(16) unsigned char tbl_bytes[]; // [32 entries][T][K] u32
     const int tid = threadIdx.x;
-    const uint64_t local = (uint64_t)blockIdx.x * BP_THREADS + tid;
+    const uint64_t local = (uint64_t)blockIdx.x * T + tid;
+    unsigned char *const my = tbl_bytes + tid * (K * 4); // this thread's slot inside entry 0
+    unsigned char *const my_lo = my + 16 * ESTRIDE;
 
-    // Zero this thread's 32 x K table words (coalesced across the warp by construction of the layout).
-#pragma unroll 4
+    // Zero this thread's 32 x K table words (a warp writes 32*K*4 contiguous bytes per entry).
+#pragma unroll 8
     for (int e = 0; e < 32; ++e) {
-        uint32_t *p = tbl + ((size_t)e * BP_THREADS + tid) * K;
 #pragma unroll
-        for (int w = 0; w < K; ++w) p[w] = 0u;
+        for (int w = 0; w < K; ++w) *reinterpret_cast<uint32_t *>(my + e * ESTRIDE + 4 * w) = 0u;
     }
     if (local >= count) return;
 
@@ -81,44 +81,118 @@ __global__ void __launch_bounds__(BP_THREADS) lev_bitpar_kernel(PairSpace ps, ui
         ps.out[pv.out_index] = n;
         return;
     }
+    const uint32_t s = 32u * K - m; // pattern symbol i lives at bit position s + i
 
-    // Build the nibble tables: bit i of HI[h][w] (LO[l][w]) is set iff pattern byte 32*w+i has high (low) nibble h (l).
-    for_each_byte_global(pat, m, [&](uint32_t i, uint32_t c) {
-        const uint32_t bit = 1u << (i & 31u);
-        uint32_t *hi = tbl + ((size_t)(c >> 4) * BP_THREADS + tid) * K + (i >> 5);
-        uint32_t *lo = tbl + ((size_t)(16u + (c & 15u)) * BP_THREADS + tid) * K + (i >> 5);
+    // ---- build the nibble tables: bit p of HI[h] (LO[l]) is set iff the symbol at position p has high (low) nibble h (l)
+    auto add_symbol = [&](uint32_t pos, uint32_t c) {
+        const uint32_t bit = 1u << (pos & 31u);
+        const uint32_t word_off = (pos >> 5) * 4u;
+        uint32_t *hi = reinterpret_cast<uint32_t *>(my + (c >> 4) * ESTRIDE + word_off);
+        uint32_t *lo = reinterpret_cast<uint32_t *>(my_lo + (c & 15u) * ESTRIDE + word_off);
         *hi |= bit;
         *lo |= bit;
-    });
+    };
+    {
+        uint32_t i = 0;
+        const uint32_t head = min(m, (uint32_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(pat) & 15u)) & 15u));
+        for (; i < head; ++i) add_symbol(s + i, ldg1(pat + i));
+        if (((s + i) & 15u) == 0u) {
+            // aligned pieces: 16 symbols share one table word and one 16-bit half of it
+            for (; i + 16 <= m; i += 16) {
+                const uint4 piece = ldg16(pat + i);
+                const uint32_t pos = s + i;
+                unsigned char *const hi_w = my + (pos >> 5) * 4u, *const lo_w = my_lo + (pos >> 5) * 4u;
+                const uint32_t bit0 = 1u << (pos & 16u);
+                const uint32_t w[4] = {piece.x, piece.y, piece.z, piece.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t wh = (w[q] >> 4) & 0x0F0F0F0Fu, wl = w[q] & 0x0F0F0F0Fu;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t bit = bit0 * (1u << (4 * q + k));
+                        uint32_t *hi = reinterpret_cast<uint32_t *>(hi_w + ((wh >> (8 * k)) & 0xFFu) * ESTRIDE);
+                        uint32_t *lo = reinterpret_cast<uint32_t *>(lo_w + ((wl >> (8 * k)) & 0xFFu) * ESTRIDE);
+                        *hi |= bit;
+                        *lo |= bit;
+                    }
+                }
+            }
+        } else {
+            for (; i + 16 <= m; i += 16) {
+                const uint4 piece = ldg16(pat + i);
+                const uint32_t w[4] = {piece.x, piece.y, piece.z, piece.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) add_symbol(s + i + 4 * q + k, (w[q] >> (8 * k)) & 0xFFu);
+            }
+        }
+        for (; i < m; ++i) add_symbol(s + i, ldg1(pat + i));
+    }
 
+    // ---- column loop
     uint32_t Pv[K], Mv[K];
 #pragma unroll
-    for (int w = 0; w < K; ++w) Pv[w] = 0xFFFFFFFFu, Mv[w] = 0u;
+    for (int w = 0; w < K; ++w) {
+        // rows below the pattern (bit < s): vertical delta 0; pattern rows: +1 (column 0 of the DP matrix)
+        const uint32_t lo_bit = 32u * w;
+        Pv[w] = s >= lo_bit + 32u ? 0u : (s <= lo_bit ? 0xFFFFFFFFu : 0xFFFFFFFFu << (s - lo_bit));
+        Mv[w] = 0u;
+    }
     uint32_t score = m;
-    const uint32_t last_word = (m - 1u) >> 5, last_bit = (m - 1u) & 31u;
 
-    for_each_byte_global(txt, n, [&](uint32_t, uint32_t c) {
+    auto step = [&](uint32_t h, uint32_t l) {
         uint32_t hi[K], lo[K];
-        load_entry<K>(tbl, (int)(c >> 4), tid, hi);
-        load_entry<K>(tbl, (int)(16u + (c & 15u)), tid, lo);
-        // Horizontal delta entering word 0 is +1 (row 0 of the DP matrix is 0,1,2,...).
-        uint32_t ph_prev = 0x80000000u, mh_prev = 0u;
+        load_words<K>(my + h * ESTRIDE, hi);
+        load_words<K>(my_lo + l * ESTRIDE, lo);
+        uint32_t hp_in = 1u, hn_in = 0u; // horizontal delta entering word 0: +1 (DP row 0 is 0,1,2,...)
 #pragma unroll
         for (int w = 0; w < K; ++w) {
-            const uint32_t eq = hi[w] & lo[w];
-            const uint32_t xv = eq | Mv[w];
-            const uint32_t eqc = eq | (mh_prev >> 31);
+            const uint32_t eqc = w == 0 ? (hi[w] & lo[w]) : ((hi[w] & lo[w]) | hn_in);
+            const uint32_t xv = (hi[w] & lo[w]) | Mv[w];
             const uint32_t xh = (((eqc & Pv[w]) + Pv[w]) ^ Pv[w]) | eqc;
             const uint32_t ph = Mv[w] | ~(xh | Pv[w]);
             const uint32_t mh = Pv[w] & xh;
-            if (w == (int)last_word || K == 1) score += ((ph >> last_bit) & 1u) - ((mh >> last_bit) & 1u);
-            const uint32_t phs = __funnelshift_l(ph_prev, ph, 1);
-            const uint32_t mhs = __funnelshift_l(mh_prev, mh, 1);
+            const uint32_t phs = ph * 2u + hp_in; // (ph << 1) | carry, on the FMA pipe
+            const uint32_t mhs = mh * 2u + hn_in;
             Pv[w] = mhs | ~(xv | phs);
             Mv[w] = phs & xv;
-            ph_prev = ph, mh_prev = mh;
+            hp_in = ph >> 31, hn_in = mh >> 31;
         }
-    });
+        score += hp_in; // the last pattern row is bit 31 of word K-1
+        score -= hn_in;
+    };
+    auto step4 = [&](uint32_t word) {
+        const uint32_t wh = (word >> 4) & 0x0F0F0F0Fu, wl = word & 0x0F0F0F0Fu;
+        step(wh & 0xFFu, wl & 0xFFu);
+        step((wh >> 8) & 0xFFu, (wl >> 8) & 0xFFu);
+        step((wh >> 16) & 0xFFu, (wl >> 16) & 0xFFu);
+        step(wh >> 24, wl >> 24);
+    };
+    {
+        uint32_t j = 0;
+        const uint32_t head = min(n, (uint32_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(txt) & 15u)) & 15u));
+        for (; j < head; ++j) {
+            const uint32_t c = ldg1(txt + j);
+            step(c >> 4, c & 15u);
+        }
+        if (j + 16 <= n) {
+            uint4 nxt = ldg16(txt + j);
+            while (j + 16 <= n) {
+                const uint4 cur = nxt;
+                if (j + 32 <= n) nxt = ldg16(txt + j + 16);
+                step4(cur.x);
+                step4(cur.y);
+                step4(cur.z);
+                step4(cur.w);
+                j += 16;
+            }
+        }
+        for (; j < n; ++j) {
+            const uint32_t c = ldg1(txt + j);
+            step(c >> 4, c & 15u);
+        }
+    }
     ps.out[pv.out_index] = score;
 }
 
