@@ -718,7 +718,8 @@ extern "C" swb_status_t swb_compute_pairs(swb_engine_t *engine, const uint8_t *a
         if ((st = enqueue_schedule_count(ctx, sh.ps, ctx.compute_stream, err)) != SWB_OK) return st;
         // data in ~8 MiB chunks so compute on chunk i overlaps the copy of chunk i+1
         const uint64_t bytes = (a_hi - a_lo) + (b_hi - b_lo);
-        int chunks = (int)std::min<uint64_t>(16, std::max<uint64_t>(1, bytes / (8ull << 20)));
+        static const uint64_t chunk_mb = getenv("SWB_CHUNK_MB") ? std::max(1, atoi(getenv("SWB_CHUNK_MB"))) : 8;
+        int chunks = (int)std::min<uint64_t>(64, std::max<uint64_t>(1, bytes / (chunk_mb << 20)));
         sh.chunk_cut.assign(chunks + 1, sh.lo);
         sh.chunk_cut[chunks] = sh.hi;
         for (int c = 1; c < chunks; ++c) sh.chunk_cut[c] = sh.lo + n * c / chunks;
