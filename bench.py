@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "250", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -247,6 +247,45 @@ def main():
     load_ms, load_n = engine.kernel_time()
     engine.set_profiling(False)
 
+    # ---- N>1: the exchange the north_star names — ONE NCCL scatter of tape slices from rank 0, per-rank compute,
+    # ONE gather of results (stringwars_b200/dist.py). Whole batch (world x n_pairs) starts resident on rank 0.
+    scatter_gather = None
+    if world > 1:
+        from stringwars_b200 import dist as swdist
+        total_pairs = n_pairs * world
+        full_a = full_b = None
+        if rank == 0:
+            fa, fb = datasets.ascii_pairs(total_pairs, length, seed=4242)
+            full_a = (torch.from_numpy(fa.data.copy()).to(device), torch.from_numpy(fa.offsets.view(np.int64).copy()).to(device))
+            full_b = (torch.from_numpy(fb.data.copy()).to(device), torch.from_numpy(fb.offsets.view(np.int64).copy()).to(device))
+
+        def sg_compute(ad, ao, bd, bo):
+            n_local = ao.numel() - 1
+            res = torch.empty(n_local, dtype=torch.int64, device=device)
+            if ad.numel() == 0:
+                ad = torch.zeros(16, dtype=torch.uint8, device=device)
+            if bd.numel() == 0:
+                bd = torch.zeros(16, dtype=torch.uint8, device=device)
+            engine.compute_pairs_device(ad.data_ptr(), ao.data_ptr(), bd.data_ptr(), bo.data_ptr(), n_local, res.data_ptr(), stream=stream.cuda_stream)
+            return res
+
+        sg_checksum = None
+
+        def sg_step(i):
+            nonlocal sg_checksum
+            res = swdist.sharded_pairs(full_a, full_b, device, sg_compute, total_pairs)
+            if res is not None and sg_checksum is None:
+                sg_checksum = int(res.sum().item())
+
+        for i in range(2):
+            sg_step(i)
+        sg_steps = max(3, min(args.steps, 10))
+        sg_dev, sg_wall = timed(sg_step, sg_steps)
+        sg_ms = max_over_ranks(max(sg_dev, sg_wall) / sg_steps)
+        scatter_gather = {"value": cells_per_pair * total_pairs / (sg_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": sg_ms,
+                          "pairs": total_pairs, "what": "batch resident on rank 0 -> one grouped NCCL send/recv scatter -> per-rank kernels -> one grouped gather",
+                          "checksum": sg_checksum}
+
     peak, peak_src = measured_peaks()
     achieved = bytes_step_alg / (kernel_ms / max(kernel_launches, 1) * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
     load_gbs = bytes_step_alg / (load_ms / max(load_n, 1) * 1e-3) / 1e9 if load_ms > 0 else 0.0
@@ -276,6 +315,8 @@ def main():
             "clocks": clocks,
             "checksum": checksum,
         }
+        if scatter_gather is not None:
+            line["scatter_gather"] = scatter_gather
         if cpu_gcups is not None:
             line["cpu_baseline"] = {"value": cpu_gcups, "unit": "GCUPS", "cores": host_threads, "kind": "port",
                                     "sample": f"{cpu_sample} pair evaluations of {length}x{length} in {cpu_dt:.1f} s ({len(a0)} distinct pairs repeated), rapidfuzz-class restatement (oracle/lev_oracle.c orc_rf_lev_bytes), {host_threads} threads"}
