@@ -57,12 +57,22 @@ class ClockSampler:
         self.gpu, self.rows, self.proc = gpu_index, [], None
 
     def start(self):
+        """Starts the poller and waits for its first row: nvidia-smi's NVML start-up takes driver locks for about a
+        second, which would otherwise land inside (and distort) a timed region that is only milliseconds long."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "250", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            deadline = time.perf_counter() + 10.0
+            while not self.rows and time.perf_counter() < deadline:
+                time.sleep(0.05)
+            self.mark()
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Forget the rows seen so far: only rows polled after this call count as 'during the timed region'."""
+        self.first = len(self.rows)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -71,10 +81,11 @@ class ClockSampler:
     def stop(self):
         if self.proc:
             self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = self.rows[getattr(self, "first", 0):] or self.rows[-1:]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
@@ -217,12 +228,22 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    if rank == 0:
+        sampler.mark()
     launches0 = sw.launch_count()
     engine.set_profiling(True)
     dev_ms, wall_ms = timed(device_step, args.steps)
     kernel_ms, kernel_launches = engine.kernel_time()
     engine.set_profiling(False)
     launches = sw.launch_count() - launches0
+    # The timed region is K x ~0.2 ms — shorter than one nvidia-smi poll. Keep the identical step running (untimed)
+    # for ~0.4 s so the clock/throttle record covers the same work under sustained load.
+    t_obs = time.perf_counter()
+    i_obs = 0
+    while time.perf_counter() - t_obs < 0.4:
+        device_step(i_obs)
+        i_obs += 1
+    torch.cuda.synchronize(device)
     kernel_name = engine.last_kernel
     # the device call synchronises once inside (schedule readback), so events and wall agree; report the larger
     step_ms = max_over_ranks(max(dev_ms, wall_ms) / args.steps)
@@ -312,7 +333,7 @@ def main():
                          "algorithmic_bytes_per_launch": bytes_step_alg,
                          "kernel_gcups": cells_step / (kernel_ms / max(kernel_launches, 1) * 1e-3) / 1e9 if kernel_ms else None,
                          "load_phase": {"kernel": "load_phase_kernel", "achieved": load_gbs, "frac": load_gbs / peak, "ms": load_ms / max(load_n, 1)}},
-            "clocks": clocks,
+            "clocks": dict(clocks or {}, note="nvidia-smi polled every 100 ms from the start of the timed region through an untimed 0.4 s continuation of the same step and the e2e region"),
             "checksum": checksum,
         }
         if scatter_gather is not None:

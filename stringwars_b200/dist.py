@@ -16,24 +16,22 @@ import torch
 import torch.distributed as dist
 
 
-def shard_bounds(offsets_a: np.ndarray, offsets_b: np.ndarray, world: int) -> List[int]:
+def shard_bounds(offsets_a, offsets_b, world: int) -> List[int]:
     """Contiguous pair ranges with balanced BYTES (bytes track cells for similar-length pairs).
-    Returns world+1 cut points; shards may be empty."""
-    n = len(offsets_a) - 1
-    total = (offsets_a - offsets_a[0]).astype(np.uint64) + (offsets_b - offsets_b[0]).astype(np.uint64)
+    Returns world+1 cut points; shards may be empty. Accepts numpy arrays or torch tensors; with device tensors
+    the prefix sums and the search stay on the device and only the world-1 cut points cross to the host."""
+    if not torch.is_tensor(offsets_a):
+        offsets_a = torch.from_numpy(np.ascontiguousarray(offsets_a).astype(np.int64))
+        offsets_b = torch.from_numpy(np.ascontiguousarray(offsets_b).astype(np.int64))
+    n = offsets_a.numel() - 1
+    total = (offsets_a - offsets_a[0]) + (offsets_b - offsets_b[0])
+    targets = (total[-1] * torch.arange(1, world, device=total.device, dtype=torch.int64)) // world
+    found = torch.searchsorted(total, targets, right=False).tolist() if world > 1 else []
     cuts = [0]
-    for r in range(1, world):
-        target = int(total[-1]) * r // world
-        cuts.append(max(cuts[-1], int(np.searchsorted(total, target, side="left"))))
+    for c in found:
+        cuts.append(max(cuts[-1], min(int(c), n)))
     cuts.append(n)
     return cuts
-
-
-def _slice_tape(data: torch.Tensor, offsets: torch.Tensor, lo: int, hi: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    o = offsets[lo: hi + 1]
-    base = int(o[0]) if hi >= lo else 0
-    end = int(o[-1]) if hi >= lo else 0
-    return data[base:end], (o - o[0]) if o.numel() else o
 
 
 def scatter_pairs(a: Optional[Tuple[torch.Tensor, torch.Tensor]], b: Optional[Tuple[torch.Tensor, torch.Tensor]],
@@ -47,17 +45,21 @@ def scatter_pairs(a: Optional[Tuple[torch.Tensor, torch.Tensor]], b: Optional[Tu
     if rank == src:
         a_data, a_offs = a
         b_data, b_offs = b
-        cuts = shard_bounds(a_offs.cpu().numpy().astype(np.uint64), b_offs.cpu().numpy().astype(np.uint64), world)
-        shards = []
+        cuts = shard_bounds(a_offs, b_offs, world)
+        idx = torch.tensor(cuts, device=a_offs.device, dtype=torch.int64)
+        a_bytes, b_bytes = a_offs[idx].tolist(), b_offs[idx].tolist()  # one small readback for all cut points
+        shards, sizes = [], []
         for r in range(world):
-            ad, ao = _slice_tape(a_data, a_offs, cuts[r], cuts[r + 1])
-            bd, bo = _slice_tape(b_data, b_offs, cuts[r], cuts[r + 1])
-            shards.append((ad.contiguous(), ao.contiguous(), bd.contiguous(), bo.contiguous()))
-            meta[4 * r: 4 * r + 4] = torch.tensor([ad.numel(), ao.numel(), bd.numel(), bo.numel()])
-        meta[4 * world:] = torch.tensor(cuts)
+            lo, hi = cuts[r], cuts[r + 1]
+            ad, bd = a_data[a_bytes[r]: a_bytes[r + 1]], b_data[b_bytes[r]: b_bytes[r + 1]]
+            ao, bo = a_offs[lo: hi + 1] - a_bytes[r], b_offs[lo: hi + 1] - b_bytes[r]
+            shards.append((ad, ao, bd, bo))
+            sizes += [ad.numel(), ao.numel(), bd.numel(), bo.numel()]
+        meta.copy_(torch.tensor(sizes + cuts, dtype=torch.int64))
     dist.broadcast(meta, src=src, group=group)
-    sizes = meta[4 * rank: 4 * rank + 4].tolist()
-    cuts = meta[4 * world:].tolist()
+    meta_host = meta.tolist()
+    sizes = meta_host[4 * rank: 4 * rank + 4]
+    cuts = meta_host[4 * world:]
     lo, hi = cuts[rank], cuts[rank + 1]
     if rank == src:
         mine = shards[src]
@@ -67,7 +69,7 @@ def scatter_pairs(a: Optional[Tuple[torch.Tensor, torch.Tensor]], b: Optional[Tu
                 continue
             for t in shards[r]:
                 if t.numel():
-                    ops.append(dist.P2POp(dist.isend, t, r, group))
+                    ops.append(dist.P2POp(dist.isend, t.contiguous(), r, group))
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
