@@ -45,8 +45,9 @@ struct AlignTables {
 };
 
 // G lanes per pair, R rows per lane. LOCAL: Smith-Waterman. AFFINE: Gotoh E/F tracks. UNARY: match/mismatch
-// constants instead of the 32x32 table.
-template <int G, int R, bool LOCAL, bool AFFINE, bool UNARY, typename BoundT>
+// constants instead of the 32x32 table. SymT: uint8_t symbols, or uint32_t for decoded UTF-8 (codepoint-level
+// Levenshtein, bench.rs:437; compared raw, `cs.ident` must be set).
+template <int G, int R, bool LOCAL, bool AFFINE, bool UNARY, typename BoundT, typename SymT = uint8_t>
 __global__ void __launch_bounds__(WF_THREADS)
     align_wavefront_kernel(PairSpace ps, uint64_t begin, uint64_t count, AlignCosts cs, const AlignTables *__restrict__ tables,
                            uint32_t slot_rows /* bytes reserved for the row string */, uint32_t slot_cols, uint32_t bound_cap) {
@@ -82,16 +83,16 @@ __global__ void __launch_bounds__(WF_THREADS)
         m = swapped ? pv.lb : pv.la;
         n = swapped ? pv.la : pv.lb;
         out_index = pv.out_index;
-        mis_r = stage_string(s_rows, rows, m, lane, G);
-        mis_c = stage_string(s_cols, cols, n, lane, G);
+        mis_r = stage_string(s_rows, rows, m * (uint32_t)sizeof(SymT), lane, G);
+        mis_c = stage_string(s_cols, cols, n * (uint32_t)sizeof(SymT), lane, G);
     }
     __syncthreads();
-    uint8_t *rows_s = s_rows + mis_r, *cols_s = s_cols + mis_c;
+    SymT *rows_s = reinterpret_cast<SymT *>(s_rows + mis_r), *cols_s = reinterpret_cast<SymT *>(s_cols + mis_c);
     const int8_t *cost_tab = s_costs + (swapped ? 1024 : 0);
     // Symbols -> classes, once, in place (the class map folds bytes into <= 32 classes, bench.rs:99-102).
-    if (need_tables) {
-        for (uint32_t i = lane; i < m; i += G) rows_s[i] = s_class[rows_s[i]];
-        for (uint32_t j = lane; j < n; j += G) cols_s[j] = s_class[cols_s[j]];
+    if (need_tables && sizeof(SymT) == 1) {
+        for (uint32_t i = lane; i < m; i += G) rows_s[i] = (SymT)s_class[(uint8_t)rows_s[i]];
+        for (uint32_t j = lane; j < n; j += G) cols_s[j] = (SymT)s_class[(uint8_t)cols_s[j]];
     }
 
     // Warp-uniform trip counts (groups of a warp may hold pairs of different sizes).
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(WF_THREADS)
         for (int r = 0; r < R; ++r) {
             const uint32_t i = row0 + r; // 0-based row
             const bool ok = strip_live && i < m;
-            rc[r] = ok ? (int)rows_s[i] : 0x7FFF;
+            rc[r] = ok ? (int)rows_s[i] : -1; // -1 is no byte, no class and no packed UTF-8 symbol
             if (ok) valid_mask |= 1u << r;
             HA[r] = HB[r] = (LOCAL || SHIFTED) ? 0 : cs.first + (int)i * cs.next; // H[i+1][0]
             Fl[r] = e_floor;

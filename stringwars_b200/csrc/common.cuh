@@ -20,11 +20,12 @@ struct PairSpace {
     uint64_t stride;       // cross mode: output row stride (elements)
     const uint32_t *order; // optional permutation (length-bucketed schedule); nullptr = identity
     uint64_t *out;         // u64 distances or i64 scores
+    uint32_t len_shift;    // log2(bytes per symbol): 0 for byte tapes, 2 for decoded UTF-8 (u32 symbols)
 };
 
 struct PairView {
-    const uint8_t *a, *b;
-    uint32_t la, lb;
+    const uint8_t *a, *b; // first byte of each string
+    uint32_t la, lb;      // lengths in SYMBOLS
     uint64_t out_index;
 };
 
@@ -41,8 +42,8 @@ __device__ __forceinline__ PairView pair_at(const PairSpace &ps, uint64_t slot) 
     uint64_t b0 = ps.b_offs[ib], b1 = ps.b_offs[ib + 1];
     v.a = ps.a_data + a0;
     v.b = ps.b_data + b0;
-    v.la = (uint32_t)(a1 - a0);
-    v.lb = (uint32_t)(b1 - b0);
+    v.la = (uint32_t)((a1 - a0) >> ps.len_shift);
+    v.lb = (uint32_t)((b1 - b0) >> ps.len_shift);
     v.out_index = oi;
     return v;
 }

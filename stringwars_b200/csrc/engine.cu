@@ -17,9 +17,12 @@
 #include <utility>
 #include <vector>
 
+#include <cub/device/device_scan.cuh>
+
 #include "align_wavefront.cuh"
 #include "lev_bitpar.cuh"
 #include "schedule.cuh"
+#include "utf8.cuh"
 
 using namespace swb;
 
@@ -82,10 +85,14 @@ struct DeviceCtx {
     int max_smem_optin = 0;
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
     ScheduleStats *d_stats = nullptr;
-    ScheduleStats *h_stats = nullptr; // pinned
-    cudaEvent_t ev_stats = nullptr, ev_offsets = nullptr;
+    ScheduleStats *h_stats = nullptr;     // pinned + mapped: the schedule kernel publishes into it directly
+    ScheduleStats *h_stats_dev = nullptr; // device alias of h_stats
+    uint32_t stats_seq = 0;               // sequence number of the last schedule launch
+    cudaStream_t stats_stream = nullptr;  // stream that launch ran on (polled for errors while waiting)
+    cudaEvent_t ev_offsets = nullptr;
     std::vector<cudaEvent_t> ev_chunks;
     DeviceBuffer order, a_data, a_offs, b_data, b_offs, out;
+    DeviceBuffer sym_a, sym_a_offs, sym_b, sym_b_offs, scan_tmp, flags; // UTF-8 engine scratch
 };
 
 struct swb_scope {
@@ -176,10 +183,10 @@ static void destroy_ctx(DeviceCtx &c) {
     if (c.compute_stream) cudaStreamDestroy(c.compute_stream);
     if (c.d_stats) cudaFree(c.d_stats);
     if (c.h_stats) cudaFreeHost(c.h_stats);
-    if (c.ev_stats) cudaEventDestroy(c.ev_stats);
     if (c.ev_offsets) cudaEventDestroy(c.ev_offsets);
     for (auto e : c.ev_chunks) cudaEventDestroy(e);
     c.order.release(), c.a_data.release(), c.a_offs.release(), c.b_data.release(), c.b_offs.release(), c.out.release();
+    c.sym_a.release(), c.sym_a_offs.release(), c.sym_b.release(), c.sym_b_offs.release(), c.scan_tmp.release(), c.flags.release();
 }
 
 extern "C" swb_status_t swb_scope_create(int first_device, int num_devices, swb_scope_t **out, const char **err) {
@@ -201,8 +208,13 @@ extern "C" swb_status_t swb_scope_create(int first_device, int num_devices, swb_
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c.compute_stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaMalloc(&c.d_stats, sizeof(ScheduleStats));
-        if (e == cudaSuccess) e = cudaHostAlloc(&c.h_stats, sizeof(ScheduleStats), cudaHostAllocDefault);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c.ev_stats, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMemset(c.d_stats, 0, sizeof(ScheduleStats));
+        if (e == cudaSuccess) e = cudaMemset(&c.d_stats->min_m, 0xFF, 2 * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaHostAlloc(&c.h_stats, sizeof(ScheduleStats), cudaHostAllocMapped);
+        if (e == cudaSuccess) {
+            memset(c.h_stats, 0, sizeof(ScheduleStats));
+            e = cudaHostGetDevicePointer((void **)&c.h_stats_dev, c.h_stats, 0);
+        }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c.ev_offsets, cudaEventDisableTiming);
         if (e != cudaSuccess) {
             for (auto &d : scope->devs) destroy_ctx(d);
@@ -280,9 +292,7 @@ extern "C" swb_status_t swb_levenshtein_create(swb_scope_t *scope, int match, in
 
 extern "C" swb_status_t swb_levenshtein_utf8_create(swb_scope_t *scope, int match, int mismatch, int open, int extend,
                                                     swb_engine_t **out, const char **err) {
-    (void)scope, (void)match, (void)mismatch, (void)open, (void)extend;
-    if (out) *out = nullptr;
-    return fail(err, SWB_UNSUPPORTED, "codepoint-level Levenshtein is not built yet (SURVEY.md §8f row 2)");
+    return lev_create(scope, match, mismatch, open, extend, ENGINE_LEVENSHTEIN_UTF8, out, err);
 }
 
 static swb_status_t align_create(swb_scope_t *scope, const uint8_t *byte_to_class, const int8_t *class_costs, int open,
@@ -399,21 +409,21 @@ static swb_status_t launch_bitpar(swb_engine *eng, DeviceCtx &ctx, const PairSpa
     return SWB_OK;
 }
 
-template <int G, int R, bool LOCAL, bool AFFINE, bool UNARY, typename BoundT>
+template <int G, int R, bool LOCAL, bool AFFINE, bool UNARY, typename BoundT, typename SymT = uint8_t>
 static swb_status_t launch_wavefront_t(swb_engine *eng, DeviceCtx &ctx, int dev_index, const PairSpace &ps, uint64_t begin,
                                        uint64_t count, const AlignCosts &cs, uint32_t max_m, uint32_t max_n,
                                        cudaStream_t stream, const char **err) {
     constexpr int PPB = WF_THREADS / G;
     constexpr bool SHIFTED = !LOCAL && !AFFINE && UNARY;
     const bool single_strip = max_m <= (uint32_t)(G * R);
-    const uint32_t slot_rows = round16(max_m + 16u) + 16u, slot_cols = round16(max_n + 16u) + 16u;
+    const uint32_t slot_rows = round16(max_m * (uint32_t)sizeof(SymT) + 16u) + 16u, slot_cols = round16(max_n * (uint32_t)sizeof(SymT) + 16u) + 16u;
     const uint32_t bound_cap = (SHIFTED && single_strip) ? 0u : max_n + 1u; // shifted single-strip cells need no boundary row
     const uint32_t bound_bytes = round16(bound_cap * (uint32_t)sizeof(BoundT) * (AFFINE ? 2u : 1u));
     const size_t smem = 2304 + (size_t)PPB * (slot_rows + slot_cols + bound_bytes);
     if (smem > (size_t)ctx.max_smem_optin)
         return fail(err, SWB_TOO_LONG, "pair of %u x %u bytes needs %zu B of shared memory per block (limit %d)", max_m, max_n,
                     smem, ctx.max_smem_optin);
-    auto kernel = align_wavefront_kernel<G, R, LOCAL, AFFINE, UNARY, BoundT>;
+    auto kernel = align_wavefront_kernel<G, R, LOCAL, AFFINE, UNARY, BoundT, SymT>;
     SWB_CUDA(allow_smem((const void *)kernel, ctx.device, smem));
     const uint64_t blocks = (count + PPB - 1) / PPB;
     {
@@ -430,6 +440,10 @@ static swb_status_t launch_wavefront_gr(swb_engine *eng, DeviceCtx &ctx, int dev
                                         uint64_t count, const AlignCosts &cs, bool local, bool affine, bool unary, bool narrow,
                                         uint32_t max_m, uint32_t max_n, cudaStream_t stream, const char **err) {
 #define SWB_WF(L, A, U, T) return launch_wavefront_t<G, R, L, A, U, T>(eng, ctx, dev_index, ps, begin, count, cs, max_m, max_n, stream, err)
+    if (ps.len_shift == 2) { // decoded UTF-8: 32-bit symbols, unit costs only
+        if (narrow) return launch_wavefront_t<G, R, false, false, true, int16_t, uint32_t>(eng, ctx, dev_index, ps, begin, count, cs, max_m, max_n, stream, err);
+        return launch_wavefront_t<G, R, false, false, true, int32_t, uint32_t>(eng, ctx, dev_index, ps, begin, count, cs, max_m, max_n, stream, err);
+    }
     if (!unary) { // general 32x32 substitution table: int32 boundary rows only
         if (!local && !affine) SWB_WF(false, false, false, int32_t);
         if (!local && affine) SWB_WF(false, true, false, int32_t);
@@ -481,7 +495,7 @@ static swb_status_t launch_wavefront(swb_engine *eng, DeviceCtx &ctx, int dev_in
 static swb_status_t launch_class(swb_engine *eng, DeviceCtx &ctx, int dev_index, const PairSpace &ps, uint64_t begin,
                                  uint64_t count, uint32_t max_m, uint32_t max_n, cudaStream_t stream, const char **err) {
     if (count == 0) return SWB_OK;
-    const bool bitpar_ok = eng->kind == ENGINE_LEVENSHTEIN && max_m <= 256;
+    const bool bitpar_ok = (eng->kind == ENGINE_LEVENSHTEIN || eng->kind == ENGINE_LEVENSHTEIN_UTF8) && ps.len_shift == 0 && max_m <= 256;
     // patterns beyond the register-resident bit-vector kernels go to the wavefront kernel (still exact)
     if (bitpar_ok && eng->algorithm != SWB_ALGO_WAVEFRONT) {
         if (max_m <= 32) return launch_bitpar<1>(eng, ctx, ps, begin, count, stream, err);
@@ -492,17 +506,39 @@ static swb_status_t launch_class(swb_engine *eng, DeviceCtx &ctx, int dev_index,
     return launch_wavefront(eng, ctx, dev_index, ps, begin, count, max_m, max_n, stream, err);
 }
 
-// Schedule counters for a device-resident PairSpace: enqueue count kernel + readback on `stream`.
+// Schedule counters for a device-resident PairSpace: enqueue the count kernel on `stream`; it publishes into
+// mapped host memory and re-arms the device counters itself (no memset / D2H copy / event on the critical path).
 static swb_status_t enqueue_schedule_count(DeviceCtx &ctx, const PairSpace &ps, cudaStream_t stream, const char **err) {
-    SWB_CUDA(cudaMemsetAsync(ctx.d_stats, 0, sizeof(ScheduleStats), stream));
-    SWB_CUDA(cudaMemsetAsync(&ctx.d_stats->min_m, 0xFF, 4, stream));
-    SWB_CUDA(cudaMemsetAsync(&ctx.d_stats->min_n, 0xFF, 4, stream));
     const unsigned blocks = (unsigned)std::min<uint64_t>((ps.n_pairs + 255) / 256, (uint64_t)ctx.sm_count * 8);
-    schedule_count_kernel<<<blocks, 256, 0, stream>>>(ps, ctx.d_stats);
+    ctx.stats_seq++;
+    if (ctx.stats_seq == 0) ctx.stats_seq = 1;
+    ctx.stats_stream = stream;
+    schedule_count_kernel<<<blocks, 256, 0, stream>>>(ps, ctx.d_stats, ctx.h_stats_dev, ctx.stats_seq);
     g_launches++;
     SWB_CUDA(cudaGetLastError());
-    SWB_CUDA(cudaMemcpyAsync(ctx.h_stats, ctx.d_stats, sizeof(ScheduleStats), cudaMemcpyDeviceToHost, stream));
-    SWB_CUDA(cudaEventRecord(ctx.ev_stats, stream));
+    return SWB_OK;
+}
+
+// Wait until the counters of the last enqueue_schedule_count are visible on the host. Spins on the sequence
+// flag (the write lands ~1-2 us after the kernel's last block); checks the stream now and then so that a failed
+// launch surfaces as an error instead of a hang.
+static swb_status_t wait_schedule_count(DeviceCtx &ctx, const char **err) {
+    volatile uint32_t *seq = &ctx.h_stats->seq;
+    for (uint64_t spins = 0; *seq != ctx.stats_seq; ++spins) {
+        if ((spins & 0x3FFF) == 0x3FFF) {
+            cudaError_t q = cudaStreamQuery(ctx.stats_stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady)
+                return fail(err, SWB_CUDA_ERROR, "schedule kernel failed: %s", cudaGetErrorString(q));
+            if (q == cudaSuccess && *seq != ctx.stats_seq) {
+                // the stream drained but the flag never arrived: treat as a device fault rather than spin forever
+                if (spins > (1ull << 26)) return fail(err, SWB_CUDA_ERROR, "schedule counters were never published");
+            }
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
     return SWB_OK;
 }
 
@@ -548,7 +584,7 @@ static swb_status_t run_device_batch(swb_engine *eng, int dev_index, PairSpace p
     ps.order = nullptr;
     swb_status_t st = enqueue_schedule_count(ctx, ps, stream, err);
     if (st != SWB_OK) return st;
-    SWB_CUDA(cudaEventSynchronize(ctx.ev_stats));
+    if ((st = wait_schedule_count(ctx, err)) != SWB_OK) return st;
     Plan plan = make_plan(*ctx.h_stats);
     if (!plan.identity) {
         SWB_CUDA(ctx.order.reserve(ps.n_pairs * sizeof(uint32_t)));
@@ -563,6 +599,66 @@ static swb_status_t run_device_batch(swb_engine *eng, int dev_index, PairSpace p
         st = launch_class(eng, ctx, dev_index, ps, plan.begin[i], plan.count[i], plan.max_m[i], plan.max_n[i], stream, err);
         if (st != SWB_OK) return st;
     }
+    return SWB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ UTF-8 engine
+
+// Split one device byte tape into 32-bit symbols (count -> scan -> pack). `offs` points at n+1 offsets valid
+// with `data` (biased pointers are fine); `total_bytes` bounds the symbol count.
+static swb_status_t decode_tape(DeviceCtx &ctx, const uint8_t *data, const uint64_t *offs, uint64_t n, uint64_t total_bytes,
+                                DeviceBuffer &sym, DeviceBuffer &sym_offs, uint32_t *d_ascii_flag, cudaStream_t stream, const char **err) {
+    SWB_CUDA(sym.reserve(total_bytes * 4 + 64));
+    SWB_CUDA(sym_offs.reserve((n + 1) * sizeof(uint64_t)));
+    size_t tmp_bytes = 0;
+    uint64_t *so = (uint64_t *)sym_offs.ptr;
+    SWB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, so, so, (int)(n + 1), stream));
+    SWB_CUDA(ctx.scan_tmp.reserve(tmp_bytes + 16));
+    const unsigned blocks = (unsigned)((n * 32 + 255) / 256);
+    utf8_count_kernel<<<blocks, 256, 0, stream>>>(data, offs, n, so, d_ascii_flag);
+    g_launches++;
+    SWB_CUDA(cudaGetLastError());
+    SWB_CUDA(cub::DeviceScan::InclusiveSum(ctx.scan_tmp.ptr, tmp_bytes, so, so, (int)(n + 1), stream));
+    utf8_pack_kernel<<<blocks, 256, 0, stream>>>(data, offs, n, so, (uint32_t *)sym.ptr);
+    g_launches++;
+    SWB_CUDA(cudaGetLastError());
+    return SWB_OK;
+}
+
+static swb_status_t run_device_batch(swb_engine *eng, int dev_index, PairSpace ps, cudaStream_t stream, const char **err);
+
+// Codepoint-level batch: decode both tapes, then either the byte kernels (all-ASCII input: bytes ARE code
+// points) or the wavefront kernel over 32-bit symbols. n_a / n_b are the string counts of the two tapes.
+static swb_status_t run_device_batch_utf8(swb_engine *eng, int dev_index, PairSpace ps, uint64_t n_a, uint64_t n_b,
+                                          uint64_t a_bytes, uint64_t b_bytes, cudaStream_t stream, const char **err) {
+    DeviceCtx &ctx = eng->scope->devs[dev_index];
+    SWB_CUDA(ctx.flags.reserve(64));
+    uint32_t *d_flag = (uint32_t *)ctx.flags.ptr;
+    SWB_CUDA(cudaMemsetAsync(d_flag, 0x01, sizeof(uint32_t), stream));
+    swb_status_t st;
+    if ((st = decode_tape(ctx, ps.a_data, ps.a_offs, n_a, a_bytes, ctx.sym_a, ctx.sym_a_offs, d_flag, stream, err)) != SWB_OK) return st;
+    const bool same_tape = ps.a_data == ps.b_data && ps.a_offs == ps.b_offs && n_a == n_b;
+    if (!same_tape)
+        if ((st = decode_tape(ctx, ps.b_data, ps.b_offs, n_b, b_bytes, ctx.sym_b, ctx.sym_b_offs, d_flag, stream, err)) != SWB_OK) return st;
+    uint32_t h_flag = 0;
+    SWB_CUDA(cudaMemcpyAsync(&h_flag, d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    SWB_CUDA(cudaStreamSynchronize(stream));
+    if (h_flag != 0) return run_device_batch(eng, dev_index, ps, stream, err); // pure ASCII
+    PairSpace sym = ps;
+    sym.a_data = (const uint8_t *)ctx.sym_a.ptr, sym.a_offs = (const uint64_t *)ctx.sym_a_offs.ptr;
+    sym.b_data = same_tape ? sym.a_data : (const uint8_t *)ctx.sym_b.ptr;
+    sym.b_offs = same_tape ? sym.a_offs : (const uint64_t *)ctx.sym_b_offs.ptr;
+    sym.len_shift = 2;
+    return run_device_batch(eng, dev_index, sym, stream, err);
+}
+
+// Total bytes spanned by n strings of a DEVICE offsets array (one small synchronous readback).
+static swb_status_t device_span(const uint64_t *offs, uint64_t n, cudaStream_t stream, uint64_t *bytes, const char **err) {
+    uint64_t ends[2] = {0, 0};
+    SWB_CUDA(cudaMemcpyAsync(&ends[0], offs, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    SWB_CUDA(cudaMemcpyAsync(&ends[1], offs + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    SWB_CUDA(cudaStreamSynchronize(stream));
+    *bytes = ends[1] - ends[0];
     return SWB_OK;
 }
 
@@ -584,6 +680,12 @@ extern "C" swb_status_t swb_compute_pairs_device(swb_engine_t *engine, int devic
     if (!a_data || !a_offsets || !b_data || !b_offsets || !out) return fail(err, SWB_INVALID_ARG, "NULL tape or output pointer");
     SWB_CUDA(cudaSetDevice(engine->scope->devs[device_index].device));
     PairSpace ps{a_data, a_offsets, b_data, b_offsets, n_pairs, 0, 0, nullptr, out};
+    if (engine->kind == ENGINE_LEVENSHTEIN_UTF8) {
+        uint64_t a_bytes = 0, b_bytes = 0;
+        if ((st = device_span(a_offsets, n_pairs, (cudaStream_t)cuda_stream, &a_bytes, err)) != SWB_OK) return st;
+        if ((st = device_span(b_offsets, n_pairs, (cudaStream_t)cuda_stream, &b_bytes, err)) != SWB_OK) return st;
+        return run_device_batch_utf8(engine, device_index, ps, n_pairs, n_pairs, a_bytes, b_bytes, (cudaStream_t)cuda_stream, err);
+    }
     return run_device_batch(engine, device_index, ps, (cudaStream_t)cuda_stream, err);
 }
 
@@ -598,6 +700,12 @@ extern "C" swb_status_t swb_compute_cross_device(swb_engine_t *engine, int devic
     if (row_stride < n_candidates) return fail(err, SWB_INVALID_ARG, "row_stride %zu < n_candidates %zu", row_stride, n_candidates);
     SWB_CUDA(cudaSetDevice(engine->scope->devs[device_index].device));
     PairSpace ps{q_data, q_offsets, c_data, c_offsets, (uint64_t)n_queries * n_candidates, n_candidates, row_stride, nullptr, out};
+    if (engine->kind == ENGINE_LEVENSHTEIN_UTF8) {
+        uint64_t a_bytes = 0, b_bytes = 0;
+        if ((st = device_span(q_offsets, n_queries, (cudaStream_t)cuda_stream, &a_bytes, err)) != SWB_OK) return st;
+        if ((st = device_span(c_offsets, n_candidates, (cudaStream_t)cuda_stream, &b_bytes, err)) != SWB_OK) return st;
+        return run_device_batch_utf8(engine, device_index, ps, n_queries, n_candidates, a_bytes, b_bytes, (cudaStream_t)cuda_stream, err);
+    }
     return run_device_batch(engine, device_index, ps, (cudaStream_t)cuda_stream, err);
 }
 
@@ -614,7 +722,7 @@ extern "C" swb_status_t swb_load_phase_device(swb_engine_t *engine, int device_i
     PairSpace ps{a_data, a_offsets, b_data, b_offsets, n_pairs, 0, 0, nullptr, out};
     st = enqueue_schedule_count(ctx, ps, stream, err);
     if (st != SWB_OK) return st;
-    SWB_CUDA(cudaEventSynchronize(ctx.ev_stats));
+    if ((st = wait_schedule_count(ctx, err)) != SWB_OK) return st;
     uint32_t max_len = 0;
     for (int c = 0; c < SCHED_MCLASSES; ++c) max_len = std::max(max_len, ctx.h_stats->max_n[c]);
     const uint32_t cap = round16((uint32_t)LOAD_PAIRS * max_len + 32u);
@@ -745,11 +853,17 @@ extern "C" swb_status_t swb_compute_pairs(swb_engine_t *engine, const uint8_t *a
         const uint64_t n = sh.hi - sh.lo;
         if (n == 0) continue;
         SWB_CUDA(cudaSetDevice(ctx.device));
-        SWB_CUDA(cudaEventSynchronize(ctx.ev_stats));
+        if ((st = wait_schedule_count(ctx, err)) != SWB_OK) return st;
         if (trace_enabled() && d == 0) t_stats = now_ms();
         Plan plan = make_plan(*ctx.h_stats);
         const int chunks = (int)sh.chunk_cut.size() - 1;
-        if (plan.identity) {
+        if (engine->kind == ENGINE_LEVENSHTEIN_UTF8) {
+            // decode needs the whole shard resident: no chunk pipelining on this path
+            SWB_CUDA(cudaStreamWaitEvent(ctx.compute_stream, ctx.ev_chunks[chunks - 1], 0));
+            if ((st = run_device_batch_utf8(engine, d, sh.ps, n, n, a_offsets[sh.hi] - a_offsets[sh.lo], b_offsets[sh.hi] - b_offsets[sh.lo],
+                                            ctx.compute_stream, err)) != SWB_OK) return st;
+            SWB_CUDA(cudaMemcpyAsync(out + sh.lo, ctx.out.ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx.compute_stream));
+        } else if (plan.identity) {
             for (int c = 0; c < chunks; ++c) {
                 const uint64_t p0 = sh.chunk_cut[c] - sh.lo, p1 = sh.chunk_cut[c + 1] - sh.lo;
                 SWB_CUDA(cudaStreamWaitEvent(ctx.compute_stream, ctx.ev_chunks[c], 0));
@@ -815,7 +929,9 @@ extern "C" swb_status_t swb_compute_cross(swb_engine_t *engine, const uint8_t *q
         SWB_CUDA(cudaEventRecord(ctx.ev_offsets, ctx.copy_stream));
         SWB_CUDA(cudaStreamWaitEvent(ctx.compute_stream, ctx.ev_offsets, 0));
         PairSpace ps{d_a - a_lo, d_q_offs + q_lo, d_b - b_lo, d_c_offs, (q_hi - q_lo) * n_candidates, n_candidates, n_candidates, nullptr, (uint64_t *)ctx.out.ptr};
-        if ((st = run_device_batch(engine, d, ps, ctx.compute_stream, err)) != SWB_OK) return st;
+        if (engine->kind == ENGINE_LEVENSHTEIN_UTF8) {
+            if ((st = run_device_batch_utf8(engine, d, ps, q_hi - q_lo, n_candidates, a_hi - a_lo, b_hi - b_lo, ctx.compute_stream, err)) != SWB_OK) return st;
+        } else if ((st = run_device_batch(engine, d, ps, ctx.compute_stream, err)) != SWB_OK) return st;
         SWB_CUDA(cudaMemcpy2DAsync(out + q_lo * row_stride, row_stride * sizeof(uint64_t), ctx.out.ptr, n_candidates * sizeof(uint64_t),
                                    n_candidates * sizeof(uint64_t), q_hi - q_lo, cudaMemcpyDeviceToHost, ctx.compute_stream));
     }

@@ -19,7 +19,9 @@ struct ScheduleStats {
     uint32_t cursor[SCHED_KEYS]; // scatter cursors (exclusive prefix of counts), written by the host-side scan
     uint32_t max_m[SCHED_MCLASSES];
     uint32_t max_n[SCHED_MCLASSES];
-    uint32_t min_m, max_m_all, min_n, max_n_all;
+    uint32_t min_m, min_n;
+    uint32_t ticket; // blocks that have merged their counters (device copy only)
+    uint32_t seq;    // host copy only: sequence number of the call whose counters are complete
 };
 
 __device__ __forceinline__ int mclass_of(uint32_t m) {
@@ -33,10 +35,14 @@ __device__ __forceinline__ int key_of(uint32_t m, uint32_t n) {
     return mclass_of(m) * SCHED_NBINS + (int)bin;
 }
 
-__global__ void __launch_bounds__(256) schedule_count_kernel(PairSpace ps, ScheduleStats *stats) {
+// `stats` (device) must be all-zero with min_* = 0xFFFFFFFF on entry; the LAST block to finish publishes the
+// merged counters into `published` (mapped, page-locked host memory: no D2H copy, no event — the host polls
+// `published->seq`) and restores `stats` to its entry state for the next call.
+__global__ void __launch_bounds__(256) schedule_count_kernel(PairSpace ps, ScheduleStats *stats, ScheduleStats *published, uint32_t seq) {
     __shared__ uint32_t s_counts[SCHED_KEYS];
     __shared__ uint32_t s_max_m[SCHED_MCLASSES], s_max_n[SCHED_MCLASSES];
     __shared__ uint32_t s_min_m, s_min_n;
+    __shared__ bool s_last;
     for (int i = threadIdx.x; i < SCHED_KEYS; i += blockDim.x) s_counts[i] = 0;
     if (threadIdx.x < SCHED_MCLASSES) s_max_m[threadIdx.x] = 0, s_max_n[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_min_m = 0xFFFFFFFFu, s_min_n = 0xFFFFFFFFu;
@@ -63,6 +69,32 @@ __global__ void __launch_bounds__(256) schedule_count_kernel(PairSpace ps, Sched
     if (threadIdx.x == 0) {
         atomicMin(&stats->min_m, s_min_m);
         atomicMin(&stats->min_n, s_min_n);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&stats->ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    volatile ScheduleStats *vs = stats;
+    for (int i = threadIdx.x; i < SCHED_KEYS; i += blockDim.x) {
+        published->counts[i] = vs->counts[i];
+        stats->counts[i] = 0;
+    }
+    if (threadIdx.x < SCHED_MCLASSES) {
+        published->max_m[threadIdx.x] = vs->max_m[threadIdx.x];
+        published->max_n[threadIdx.x] = vs->max_n[threadIdx.x];
+        stats->max_m[threadIdx.x] = 0, stats->max_n[threadIdx.x] = 0;
+    }
+    if (threadIdx.x == 0) {
+        published->min_m = vs->min_m, published->min_n = vs->min_n;
+        stats->min_m = 0xFFFFFFFFu, stats->min_n = 0xFFFFFFFFu, stats->ticket = 0;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *reinterpret_cast<volatile uint32_t *>(&published->seq) = seq;
+        __threadfence_system();
     }
 }
 

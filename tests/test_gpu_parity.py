@@ -205,3 +205,51 @@ def test_multi_device_scope_matches_single(scope, lev, oracle):
     multi_scope = sw.DeviceScope.gpu_devices(0, sw.device_count())
     multi = sw.LevenshteinDistances(multi_scope).compute_pairs(multi_scope, a, b)
     assert np.array_equal(single, multi)
+
+
+# ---------------------------------------------------------------- codepoint-level (UTF-8) engine
+
+@pytest.fixture(scope="module")
+def lev_utf8(scope):
+    return sw.LevenshteinDistancesUtf8(scope, 0, 1, 1, 1)
+
+
+def test_utf8_engine_config3_lines(scope, lev_utf8, oracle):
+    """`LevenshteinDistancesUtf8` / `rapidfuzz ... distance(a.chars(), b.chars())` (bench.rs:386-399, 437)."""
+    a, b = datasets.utf8_line_pairs(3000)
+    got = lev_utf8.compute_pairs(scope, a, b)
+    want = oracle.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, oracle.UTF8, threads=8)
+    bad = np.flatnonzero(got != want)
+    assert bad.size == 0, (bad[:5], got[bad[:5]], want[bad[:5]], lev_utf8.last_kernel)
+    assert "wavefront" in lev_utf8.last_kernel
+    # codepoint-level differs from byte-level on multi-byte text, so this is not accidentally the byte path
+    assert (got != oracle.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, threads=8)).any()
+
+
+def test_utf8_engine_known_answers_and_edges(scope, lev_utf8, oracle):
+    sa = ["naïve", "", "日本語テキスト", "😀😃😄", "abc", "Привет, мир", "é" * 40, "a" * 70, "ß", ""]
+    sb = ["naive", "añb", "日本語のテキスト", "😀😄", "abc", "Привет мир!", "e" * 41, "ä" * 70, "ss", ""]
+    a, b = BytesTape.from_strings(sa), BytesTape.from_strings(sb)
+    got = lev_utf8.compute_pairs(scope, a, b)
+    want = oracle.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, oracle.UTF8)
+    assert np.array_equal(got, want)
+    assert list(got[:5]) == [1, 3, 1, 1, 0]
+
+
+def test_utf8_engine_ascii_shortcut_and_golden(scope, lev_utf8, oracle, golden):
+    a, b = datasets.ascii_pairs(20_000, 64, seed=12)
+    got = lev_utf8.compute_pairs(scope, a, b)
+    assert np.array_equal(got, oracle.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, threads=8))
+    assert "bitpar" in lev_utf8.last_kernel  # pure ASCII: bytes are code points, the byte kernels run
+    cases = [c for c in golden if "chars" in c]
+    ga = BytesTape.from_strings([bytes.fromhex(c["a"]) for c in cases])
+    gb = BytesTape.from_strings([bytes.fromhex(c["b"]) for c in cases])
+    assert np.array_equal(lev_utf8.compute_pairs(scope, ga, gb), np.array([c["chars"] for c in cases], dtype=np.uint64))
+
+
+def test_utf8_engine_cross(scope, lev_utf8, oracle):
+    tape = datasets.utf8_line_pairs(120, 20, 90, seed=9)[0]
+    q, c = tape.subview(0, 60), tape.subview(60, 120)
+    got = lev_utf8.compute(scope, q, c)
+    want = oracle.levenshtein_cross(q.data, q.offsets, c.data, c.offsets, oracle.UTF8, threads=8)
+    assert np.array_equal(got, want)
