@@ -35,18 +35,27 @@ struct BitparConfig {
     static constexpr int THREADS = K <= 4 ? 128 : 64; // 128 * K bytes of tables per thread
 };
 
-// K table words of the entry at `p` (shared memory).
-template <int K>
-__device__ __forceinline__ void load_words(const unsigned char *p, uint32_t (&w)[K]) {
+// Byte offset of word w of THIS thread inside a table entry. K <= 4: the thread's K words are contiguous
+// ([thread][K]); K = 8: two 4-word parts, each part [thread][4], so that every LDS.128 of a warp covers 512
+// contiguous bytes (a [thread][8] layout would put 32-byte strides under 16-byte loads: 2-way bank conflicts).
+template <int K, int T>
+__device__ __forceinline__ uint32_t word_offset(int tid, uint32_t w) {
+    if constexpr (K <= 4) return (uint32_t)tid * (K * 4) + w * 4u;
+    else return (w >> 2) * (T * 16u) + (uint32_t)tid * 16u + (w & 3u) * 4u;
+}
+
+// K table words of the entry that starts at `entry` (shared memory) for thread `tid`.
+template <int K, int T>
+__device__ __forceinline__ void load_words(const unsigned char *entry, int tid, uint32_t (&w)[K]) {
     if constexpr (K == 1) {
-        w[0] = *reinterpret_cast<const uint32_t *>(p);
+        w[0] = *reinterpret_cast<const uint32_t *>(entry + tid * 4);
     } else if constexpr (K == 2) {
-        const uint2 v = *reinterpret_cast<const uint2 *>(p);
+        const uint2 v = *reinterpret_cast<const uint2 *>(entry + tid * 8);
         w[0] = v.x, w[1] = v.y;
     } else {
 #pragma unroll
         for (int q = 0; q < K / 4; ++q) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(p + 16 * q);
+            const uint4 v = *reinterpret_cast<const uint4 *>(entry + (K == 4 ? 0 : q * T * 16) + tid * 16);
             w[4 * q + 0] = v.x, w[4 * q + 1] = v.y, w[4 * q + 2] = v.z, w[4 * q + 3] = v.w;
         }
     }
@@ -59,14 +68,13 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
     extern __shared__ __align__(16) unsigned char tbl_bytes[]; // [32 entries][T][K] u32
     const int tid = threadIdx.x;
     const uint64_t local = (uint64_t)blockIdx.x * T + tid;
-    unsigned char *const my = tbl_bytes + tid * (K * 4); // this thread's slot inside entry 0
-    unsigned char *const my_lo = my + 16 * ESTRIDE;
+    unsigned char *const tbl_hi = tbl_bytes, *const tbl_lo = tbl_bytes + 16 * ESTRIDE;
 
-    // Zero this thread's 32 x K table words (a warp writes 32*K*4 contiguous bytes per entry).
+    // Zero this thread's 32 x K table words.
 #pragma unroll 8
     for (int e = 0; e < 32; ++e) {
 #pragma unroll
-        for (int w = 0; w < K; ++w) *reinterpret_cast<uint32_t *>(my + e * ESTRIDE + 4 * w) = 0u;
+        for (int w = 0; w < K; ++w) *reinterpret_cast<uint32_t *>(tbl_bytes + e * ESTRIDE + word_offset<K, T>(tid, w)) = 0u;
     }
     if (local >= count) return;
 
@@ -86,9 +94,9 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
     // ---- build the nibble tables: bit p of HI[h] (LO[l]) is set iff the symbol at position p has high (low) nibble h (l)
     auto add_symbol = [&](uint32_t pos, uint32_t c) {
         const uint32_t bit = 1u << (pos & 31u);
-        const uint32_t word_off = (pos >> 5) * 4u;
-        uint32_t *hi = reinterpret_cast<uint32_t *>(my + (c >> 4) * ESTRIDE + word_off);
-        uint32_t *lo = reinterpret_cast<uint32_t *>(my_lo + (c & 15u) * ESTRIDE + word_off);
+        const uint32_t word_off = word_offset<K, T>(tid, pos >> 5);
+        uint32_t *hi = reinterpret_cast<uint32_t *>(tbl_hi + (c >> 4) * ESTRIDE + word_off);
+        uint32_t *lo = reinterpret_cast<uint32_t *>(tbl_lo + (c & 15u) * ESTRIDE + word_off);
         *hi |= bit;
         *lo |= bit;
     };
@@ -101,7 +109,7 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
             for (; i + 16 <= m; i += 16) {
                 const uint4 piece = ldg16(pat + i);
                 const uint32_t pos = s + i;
-                unsigned char *const hi_w = my + (pos >> 5) * 4u, *const lo_w = my_lo + (pos >> 5) * 4u;
+                unsigned char *const hi_w = tbl_hi + word_offset<K, T>(tid, pos >> 5), *const lo_w = tbl_lo + word_offset<K, T>(tid, pos >> 5);
                 const uint32_t bit0 = 1u << (pos & 16u);
                 const uint32_t w[4] = {piece.x, piece.y, piece.z, piece.w};
 #pragma unroll
@@ -143,8 +151,8 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
 
     auto step = [&](uint32_t h, uint32_t l) {
         uint32_t hi[K], lo[K];
-        load_words<K>(my + h * ESTRIDE, hi);
-        load_words<K>(my_lo + l * ESTRIDE, lo);
+        load_words<K, T>(tbl_hi + h * ESTRIDE, tid, hi);
+        load_words<K, T>(tbl_lo + l * ESTRIDE, tid, lo);
         uint32_t hp_in = 1u, hn_in = 0u; // horizontal delta entering word 0: +1 (DP row 0 is 0,1,2,...)
 #pragma unroll
         for (int w = 0; w < K; ++w) {

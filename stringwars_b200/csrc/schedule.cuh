@@ -47,17 +47,44 @@ __global__ void __launch_bounds__(256) schedule_count_kernel(PairSpace ps, Sched
     if (threadIdx.x < SCHED_MCLASSES) s_max_m[threadIdx.x] = 0, s_max_n[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_min_m = 0xFFFFFFFFu, s_min_n = 0xFFFFFFFFu;
     __syncthreads();
+    // Threads keep a run (key, count, extrema) in registers and touch shared memory only when the key changes;
+    // a warp whose lanes all ended on the same key merges with warp reductions and ONE set of atomics. Uniform
+    // batches (every pair the same key) would otherwise serialise a million atomics on a single counter.
+    int run_key = -1;
+    uint32_t run_count = 0, run_max_m = 0, run_max_n = 0, run_min_m = 0xFFFFFFFFu, run_min_n = 0xFFFFFFFFu;
+    auto flush = [&](int key, uint32_t count, uint32_t mx_m, uint32_t mx_n, uint32_t mn_m, uint32_t mn_n) {
+        if (key < 0) return;
+        const int c = key / SCHED_NBINS;
+        atomicAdd(&s_counts[key], count);
+        atomicMax(&s_max_m[c], mx_m);
+        atomicMax(&s_max_n[c], mx_n);
+        atomicMin(&s_min_m, mn_m);
+        atomicMin(&s_min_n, mn_n);
+    };
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < ps.n_pairs; k += (uint64_t)gridDim.x * blockDim.x) {
         PairSpace id = ps;
         id.order = nullptr;
         const PairView pv = pair_at(id, k);
         const uint32_t m = min(pv.la, pv.lb), n = max(pv.la, pv.lb);
-        const int c = mclass_of(m);
-        atomicAdd(&s_counts[key_of(m, n)], 1u);
-        atomicMax(&s_max_m[c], m);
-        atomicMax(&s_max_n[c], n);
-        atomicMin(&s_min_m, m);
-        atomicMin(&s_min_n, n);
+        const int key = key_of(m, n);
+        if (key != run_key) {
+            flush(run_key, run_count, run_max_m, run_max_n, run_min_m, run_min_n);
+            run_key = key, run_count = 0, run_max_m = 0, run_max_n = 0, run_min_m = 0xFFFFFFFFu, run_min_n = 0xFFFFFFFFu;
+        }
+        run_count += 1;
+        run_max_m = max(run_max_m, m), run_max_n = max(run_max_n, n);
+        run_min_m = min(run_min_m, m), run_min_n = min(run_min_n, n);
+    }
+    {
+        const int key0 = __shfl_sync(0xffffffffu, run_key, 0);
+        if (__all_sync(0xffffffffu, run_key == key0)) {
+            const uint32_t count = __reduce_add_sync(0xffffffffu, run_count);
+            const uint32_t mx_m = __reduce_max_sync(0xffffffffu, run_max_m), mx_n = __reduce_max_sync(0xffffffffu, run_max_n);
+            const uint32_t mn_m = __reduce_min_sync(0xffffffffu, run_min_m), mn_n = __reduce_min_sync(0xffffffffu, run_min_n);
+            if ((threadIdx.x & 31) == 0) flush(key0, count, mx_m, mx_n, mn_m, mn_n);
+        } else {
+            flush(run_key, run_count, run_max_m, run_max_n, run_min_m, run_min_n);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < SCHED_KEYS; i += blockDim.x)
@@ -110,8 +137,9 @@ __global__ void __launch_bounds__(256) schedule_scatter_kernel(PairSpace ps, Sch
 }
 
 // Pair-load phase on its own: a block stages the bytes of LOAD_PAIRS consecutive pairs (both tapes) into
-// shared memory with coalesced, aligned 16-byte loads, then thread p byte-sums pair p out of shared memory.
-// Moves exactly the algorithmic bytes of the compute kernels' load phase (+ offsets in, 8 B/pair out).
+// shared memory — one TMA bulk copy per tape span, completion on an mbarrier — then thread p byte-sums pair p
+// out of shared memory. Moves exactly the algorithmic bytes of the compute kernels' load phase (+ offsets in,
+// 8 B/pair out).
 constexpr int LOAD_THREADS = 256;
 constexpr int LOAD_PAIRS = 256;
 
@@ -132,17 +160,41 @@ __device__ __forceinline__ uint32_t masked_sum16(const uint8_t *piece, int lo, i
     return acc;
 }
 
+// 1-D bulk async copy global -> shared (TMA, `cp.async.bulk`, SASS UBLKCP) completing on an mbarrier.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(mbar))
+                 : "memory");
+}
+
 __global__ void __launch_bounds__(LOAD_THREADS) load_phase_kernel(PairSpace ps, uint32_t cap_a, uint32_t cap_b) {
-    extern __shared__ __align__(16) uint8_t lsm[];
+    extern __shared__ __align__(128) uint8_t lsm[];
+    __shared__ __align__(8) uint64_t mbar;
     uint8_t *s_a = lsm, *s_b = lsm + cap_a;
     const uint64_t p0 = (uint64_t)blockIdx.x * LOAD_PAIRS;
     const uint64_t p1 = min(p0 + (uint64_t)LOAD_PAIRS, ps.n_pairs);
     const uint64_t a_lo = ps.a_offs[p0], a_hi = ps.a_offs[p1], b_lo = ps.b_offs[p0], b_hi = ps.b_offs[p1];
     const uint8_t *ga = ps.a_data + a_lo, *gb = ps.b_data + b_lo;
     const uint32_t mis_a = (uint32_t)(reinterpret_cast<uintptr_t>(ga) & 15u), mis_b = (uint32_t)(reinterpret_cast<uintptr_t>(gb) & 15u);
-    stage_string(s_a, ga, (uint32_t)(a_hi - a_lo), threadIdx.x, LOAD_THREADS);
-    stage_string(s_b, gb, (uint32_t)(b_hi - b_lo), threadIdx.x, LOAD_THREADS);
+    // whole 16-byte pieces covering each span, exactly what the compute kernels' staging loads touch
+    const uint32_t bytes_a = a_hi > a_lo ? ((mis_a + (uint32_t)(a_hi - a_lo) + 15u) & ~15u) : 0u;
+    const uint32_t bytes_b = b_hi > b_lo ? ((mis_b + (uint32_t)(b_hi - b_lo) + 15u) & ~15u) : 0u;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes_a + bytes_b) : "memory");
+        if (bytes_a) bulk_g2s(s_a, ga - mis_a, bytes_a, &mbar);
+        if (bytes_b) bulk_g2s(s_b, gb - mis_b, bytes_b, &mbar);
+    }
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
+    }
     const uint64_t p = p0 + threadIdx.x;
     if (p < p1) {
         uint32_t acc = 0;

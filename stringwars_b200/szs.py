@@ -16,6 +16,7 @@ no compute and no fallback. Errors surface as `stringwars_b200.Error` carrying t
 from __future__ import annotations
 
 import ctypes
+import weakref
 from typing import Optional
 
 import numpy as np
@@ -51,6 +52,7 @@ class DeviceScope:
         err = ctypes.c_char_p()
         _lib.check(_lib.lib().swb_scope_create(first_device, num_devices, ctypes.byref(self._h), ctypes.byref(err)), err)
         self.first_device, self.num_devices = first_device, num_devices
+        self._engines = weakref.WeakSet()  # engines hold device state owned by the scope: they are closed first
 
     @classmethod
     def gpu_device(cls, device: int = 0) -> "DeviceScope":
@@ -66,6 +68,8 @@ class DeviceScope:
 
     def close(self) -> None:
         if self._h:
+            for engine in list(self._engines):
+                engine.close()
             _lib.lib().swb_scope_destroy(self._h)
             self._h = ctypes.c_void_p()
 
@@ -86,6 +90,7 @@ class _Engine:
     def __init__(self, scope: DeviceScope):
         self._scope = scope  # keeps the scope alive for the engine's lifetime
         self._h = ctypes.c_void_p()
+        scope._engines.add(self)
 
     # ---- options
     def set_algorithm(self, algorithm: int) -> "_Engine":
