@@ -21,6 +21,7 @@
 
 #include "align_wavefront.cuh"
 #include "lev_bitpar.cuh"
+#include "lev_bitpar_coop.cuh"
 #include "schedule.cuh"
 #include "utf8.cuh"
 
@@ -409,6 +410,26 @@ static swb_status_t launch_bitpar(swb_engine *eng, DeviceCtx &ctx, const PairSpa
     return SWB_OK;
 }
 
+// Returns SWB_TOO_LONG (without launching) when the staged strings do not fit in shared memory.
+template <int G, int K>
+static swb_status_t launch_bitpar_coop(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count,
+                                       uint32_t max_m, uint32_t max_n, const char *name, cudaStream_t stream, const char **err) {
+    constexpr int PPB = BPC_THREADS / G;
+    const uint32_t slot_rows = round16(max_m + 16u) + 16u, slot_cols = round16(max_n + 16u) + 16u;
+    const size_t smem = (size_t)32 * BPC_THREADS * K * 4 + (size_t)PPB * (slot_rows + slot_cols);
+    if (smem > (size_t)ctx.max_smem_optin) return fail(err, SWB_TOO_LONG, "strings of %u x %u bytes do not fit the bit-parallel kernel's shared memory", max_m, max_n);
+    SWB_CUDA(allow_smem((const void *)lev_bitpar_coop_kernel<G, K>, ctx.device, smem));
+    const uint64_t blocks = (count + PPB - 1) / PPB;
+    {
+        ProfileBracket bracket(eng, ctx.device, stream);
+        lev_bitpar_coop_kernel<G, K><<<(unsigned)blocks, BPC_THREADS, smem, stream>>>(ps, begin, count, slot_rows, slot_cols);
+    }
+    g_launches++;
+    eng->last_kernel = name;
+    SWB_CUDA(cudaGetLastError());
+    return SWB_OK;
+}
+
 template <int G, int R, bool LOCAL, bool AFFINE, bool UNARY, typename BoundT, typename SymT = uint8_t>
 static swb_status_t launch_wavefront_t(swb_engine *eng, DeviceCtx &ctx, int dev_index, const PairSpace &ps, uint64_t begin,
                                        uint64_t count, const AlignCosts &cs, uint32_t max_m, uint32_t max_n,
@@ -495,13 +516,20 @@ static swb_status_t launch_wavefront(swb_engine *eng, DeviceCtx &ctx, int dev_in
 static swb_status_t launch_class(swb_engine *eng, DeviceCtx &ctx, int dev_index, const PairSpace &ps, uint64_t begin,
                                  uint64_t count, uint32_t max_m, uint32_t max_n, cudaStream_t stream, const char **err) {
     if (count == 0) return SWB_OK;
-    const bool bitpar_ok = (eng->kind == ENGINE_LEVENSHTEIN || eng->kind == ENGINE_LEVENSHTEIN_UTF8) && ps.len_shift == 0 && max_m <= 256;
-    // patterns beyond the register-resident bit-vector kernels go to the wavefront kernel (still exact)
-    if (bitpar_ok && eng->algorithm != SWB_ALGO_WAVEFRONT) {
+    const bool lev_bytes = (eng->kind == ENGINE_LEVENSHTEIN || eng->kind == ENGINE_LEVENSHTEIN_UTF8) && ps.len_shift == 0;
+    if (lev_bytes && eng->algorithm != SWB_ALGO_WAVEFRONT) {
+        // thread-per-pair bit-vector kernels up to 256 pattern bytes, lane-group kernels up to 4096
         if (max_m <= 32) return launch_bitpar<1>(eng, ctx, ps, begin, count, stream, err);
         if (max_m <= 64) return launch_bitpar<2>(eng, ctx, ps, begin, count, stream, err);
         if (max_m <= 128) return launch_bitpar<4>(eng, ctx, ps, begin, count, stream, err);
-        return launch_bitpar<8>(eng, ctx, ps, begin, count, stream, err);
+        if (max_m <= 256) return launch_bitpar<8>(eng, ctx, ps, begin, count, stream, err);
+        swb_status_t st = SWB_TOO_LONG;
+        if (max_m <= 512) st = launch_bitpar_coop<8, 2>(eng, ctx, ps, begin, count, max_m, max_n, "lev_bitpar_coop<G=8,K=2>", stream, err);
+        else if (max_m <= 1024) st = launch_bitpar_coop<16, 2>(eng, ctx, ps, begin, count, max_m, max_n, "lev_bitpar_coop<G=16,K=2>", stream, err);
+        else if (max_m <= 2048) st = launch_bitpar_coop<32, 2>(eng, ctx, ps, begin, count, max_m, max_n, "lev_bitpar_coop<G=32,K=2>", stream, err);
+        else if (max_m <= 4096) st = launch_bitpar_coop<32, 4>(eng, ctx, ps, begin, count, max_m, max_n, "lev_bitpar_coop<G=32,K=4>", stream, err);
+        if (st != SWB_TOO_LONG) return st;
+        // beyond the lane-group kernels' capacity: the wavefront kernel's row strips (still exact)
     }
     return launch_wavefront(eng, ctx, dev_index, ps, begin, count, max_m, max_n, stream, err);
 }

@@ -253,3 +253,23 @@ def test_utf8_engine_cross(scope, lev_utf8, oracle):
     got = lev_utf8.compute(scope, q, c)
     want = oracle.levenshtein_cross(q.data, q.offsets, c.data, c.offsets, oracle.UTF8, threads=8)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("algo", [sw.ALGO_AUTO, sw.ALGO_WAVEFRONT])
+def test_very_long_and_lopsided_pairs(scope, lev, oracle, algo):
+    """Lane-group bit-vector kernels up to 4096 pattern bytes, wavefront row strips beyond, short-vs-long pairs."""
+    rng = np.random.default_rng(23)
+    alphabet = np.frombuffer(b"ACGT", dtype=np.uint8)
+    la = np.array([300, 512, 513, 1024, 1025, 2048, 2500, 4096, 4097, 5000, 7, 64, 1, 0, 700, 3000])
+    lb = np.array([511, 512, 700, 1024, 2000, 2048, 2600, 4096, 4100, 5000, 3000, 4000, 5000, 900, 13, 257])
+    a = datasets._ragged(la, alphabet, rng, False)
+    b = datasets._ragged(lb, alphabet, rng, False)
+    _check_pairs(lev, scope, oracle, a, b, algo)
+    # similar strings: small distances through the long kernels
+    base = bytes(rng.choice(alphabet, size=3000))
+    edits = bytearray(base)
+    for pos in rng.choice(3000, size=40, replace=False):
+        edits[pos] = ord("N")
+    a2, b2 = BytesTape.from_strings([base, base[:2000], base]), BytesTape.from_strings([bytes(edits), bytes(edits), base[5:]])
+    got = _check_pairs(lev, scope, oracle, a2, b2, algo)
+    assert got[0] == 40 and got[2] == 5
