@@ -498,18 +498,22 @@ static swb_status_t launch_wavefront(swb_engine *eng, DeviceCtx &ctx, int dev_in
     if (eng->unary) maxabs = std::max(maxabs, std::max(std::abs(cs.match), std::abs(cs.mismatch)));
     else maxabs = std::max(maxabs, 128);
     const bool narrow = (uint64_t)(max_m + max_n + 2u) * 3u * (uint64_t)maxabs < 30000u;
-#define SWB_GR(G, R, NAME)                                                                                           \
-    do {                                                                                                           \
-        eng->last_kernel = NAME;                                                                                   \
-        return launch_wavefront_gr<G, R>(eng, ctx, dev_index, ps, begin, count, cs, local, affine, eng->unary, narrow, max_m, max_n, stream, err); \
-    } while (0)
-    if (max_m <= 16) SWB_GR(1, 16, "align_wavefront<G=1,R=16>");
-    if (max_m <= 32) SWB_GR(2, 16, "align_wavefront<G=2,R=16>");
-    if (max_m <= 64) SWB_GR(4, 16, "align_wavefront<G=4,R=16>");
-    if (max_m <= 128) SWB_GR(8, 16, "align_wavefront<G=8,R=16>");
-    if (max_m <= 256) SWB_GR(16, 16, "align_wavefront<G=16,R=16>");
-    SWB_GR(32, 16, "align_wavefront<G=32,R=16>");
+    // Narrowest group that covers the pattern in one strip; if the class's longest text makes the block's staged
+    // strings overflow shared memory (lopsided pairs), widen the group: fewer pairs per block, same kernel.
+    swb_status_t st = SWB_TOO_LONG;
+#define SWB_GR(G, R, NAME)                                                                                                              \
+    if (st == SWB_TOO_LONG && (max_m <= (uint32_t)(G) * (R) || (G) == 32)) {                                                              \
+        eng->last_kernel = NAME;                                                                                                        \
+        st = launch_wavefront_gr<G, R>(eng, ctx, dev_index, ps, begin, count, cs, local, affine, eng->unary, narrow, max_m, max_n, stream, err); \
+    }
+    SWB_GR(1, 16, "align_wavefront<G=1,R=16>")
+    SWB_GR(2, 16, "align_wavefront<G=2,R=16>")
+    SWB_GR(4, 16, "align_wavefront<G=4,R=16>")
+    SWB_GR(8, 16, "align_wavefront<G=8,R=16>")
+    SWB_GR(16, 16, "align_wavefront<G=16,R=16>")
+    SWB_GR(32, 16, "align_wavefront<G=32,R=16>")
 #undef SWB_GR
+    return st;
 }
 
 // One length class of one batch on one device.
@@ -753,13 +757,17 @@ extern "C" swb_status_t swb_load_phase_device(swb_engine_t *engine, int device_i
     if ((st = wait_schedule_count(ctx, err)) != SWB_OK) return st;
     uint32_t max_len = 0;
     for (int c = 0; c < SCHED_MCLASSES; ++c) max_len = std::max(max_len, ctx.h_stats->max_n[c]);
-    const uint32_t cap = round16((uint32_t)LOAD_PAIRS * max_len + 32u);
-    const size_t smem = 2 * (size_t)cap;
-    if (smem > (size_t)ctx.max_smem_optin) return fail(err, SWB_TOO_LONG, "load-phase kernel supports strings up to %d bytes", ctx.max_smem_optin / (2 * LOAD_PAIRS));
+    const uint32_t cap = (round16((uint32_t)LOAD_PAIRS * max_len + 32u) + 127u) & ~127u;
+    const size_t smem = 4 * (size_t)cap; // two stages x (a span + b span)
+    if (smem > (size_t)ctx.max_smem_optin) return fail(err, SWB_TOO_LONG, "load-phase kernel supports strings up to %d bytes", ctx.max_smem_optin / (4 * LOAD_PAIRS));
     SWB_CUDA(allow_smem((const void *)load_phase_kernel, ctx.device, smem));
     {
+        // persistent grid: as many CTAs as fit (shared memory bound), never more than there are tiles
+        const uint64_t tiles = (n_pairs + LOAD_PAIRS - 1) / LOAD_PAIRS;
+        const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (size_t)(ctx.max_smem_optin - 1024) / (smem + 1024)));
+        const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)ctx.sm_count * per_sm);
         ProfileBracket bracket(engine, ctx.device, stream);
-        load_phase_kernel<<<(unsigned)((n_pairs + LOAD_PAIRS - 1) / LOAD_PAIRS), LOAD_THREADS, smem, stream>>>(ps, cap, cap);
+        load_phase_kernel<<<grid, LOAD_THREADS, smem, stream>>>(ps, cap, cap);
     }
     g_launches++;
     engine->last_kernel = "load_phase";

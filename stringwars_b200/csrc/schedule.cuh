@@ -168,47 +168,74 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
+struct LoadTileMeta {
+    uint32_t mis_a, mis_b; // misalignment of the tile's first byte inside its first 16-byte piece
+    uint64_t a_lo, b_lo;   // tape offsets of the tile's first strings
+};
+
+// Persistent CTAs, two shared-memory stages: while the threads byte-sum tile i out of stage i&1, the TMA engine
+// is already filling stage (i+1)&1 with tile i+gridDim.x. Per-pair offsets are fetched before waiting on the
+// mbarrier so their latency hides behind the bulk copy.
 __global__ void __launch_bounds__(LOAD_THREADS) load_phase_kernel(PairSpace ps, uint32_t cap_a, uint32_t cap_b) {
     extern __shared__ __align__(128) uint8_t lsm[];
-    __shared__ __align__(8) uint64_t mbar;
-    uint8_t *s_a = lsm, *s_b = lsm + cap_a;
-    const uint64_t p0 = (uint64_t)blockIdx.x * LOAD_PAIRS;
-    const uint64_t p1 = min(p0 + (uint64_t)LOAD_PAIRS, ps.n_pairs);
-    const uint64_t a_lo = ps.a_offs[p0], a_hi = ps.a_offs[p1], b_lo = ps.b_offs[p0], b_hi = ps.b_offs[p1];
-    const uint8_t *ga = ps.a_data + a_lo, *gb = ps.b_data + b_lo;
-    const uint32_t mis_a = (uint32_t)(reinterpret_cast<uintptr_t>(ga) & 15u), mis_b = (uint32_t)(reinterpret_cast<uintptr_t>(gb) & 15u);
-    // whole 16-byte pieces covering each span, exactly what the compute kernels' staging loads touch
-    const uint32_t bytes_a = a_hi > a_lo ? ((mis_a + (uint32_t)(a_hi - a_lo) + 15u) & ~15u) : 0u;
-    const uint32_t bytes_b = b_hi > b_lo ? ((mis_b + (uint32_t)(b_hi - b_lo) + 15u) & ~15u) : 0u;
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ LoadTileMeta meta[2];
+    const uint32_t stage_bytes = cap_a + cap_b;
+    const uint64_t tiles = (ps.n_pairs + LOAD_PAIRS - 1) / LOAD_PAIRS;
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[1])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    auto issue = [&](uint64_t tile, int stage) { // thread 0 only
+        const uint64_t p0 = tile * LOAD_PAIRS, p1 = min(p0 + (uint64_t)LOAD_PAIRS, ps.n_pairs);
+        const uint64_t a_lo = ps.a_offs[p0], a_hi = ps.a_offs[p1], b_lo = ps.b_offs[p0], b_hi = ps.b_offs[p1];
+        const uint8_t *ga = ps.a_data + a_lo, *gb = ps.b_data + b_lo;
+        const uint32_t mis_a = (uint32_t)(reinterpret_cast<uintptr_t>(ga) & 15u), mis_b = (uint32_t)(reinterpret_cast<uintptr_t>(gb) & 15u);
+        // whole 16-byte pieces covering each span: exactly what the compute kernels' staging loads touch
+        const uint32_t bytes_a = a_hi > a_lo ? ((mis_a + (uint32_t)(a_hi - a_lo) + 15u) & ~15u) : 0u;
+        const uint32_t bytes_b = b_hi > b_lo ? ((mis_b + (uint32_t)(b_hi - b_lo) + 15u) & ~15u) : 0u;
+        meta[stage] = LoadTileMeta{mis_a, mis_b, a_lo, b_lo};
+        uint8_t *s_a = lsm + (size_t)stage * stage_bytes, *s_b = s_a + cap_a;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar[stage])), "r"(bytes_a + bytes_b) : "memory");
+        if (bytes_a) bulk_g2s(s_a, ga - mis_a, bytes_a, &mbar[stage]);
+        if (bytes_b) bulk_g2s(s_b, gb - mis_b, bytes_b, &mbar[stage]);
+    };
     __syncthreads();
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes_a + bytes_b) : "memory");
-        if (bytes_a) bulk_g2s(s_a, ga - mis_a, bytes_a, &mbar);
-        if (bytes_b) bulk_g2s(s_b, gb - mis_b, bytes_b, &mbar);
-    }
-    {
-        uint32_t done = 0;
-        while (!done)
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
-    }
-    const uint64_t p = p0 + threadIdx.x;
-    if (p < p1) {
-        uint32_t acc = 0;
+    if (threadIdx.x == 0 && blockIdx.x < tiles) issue(blockIdx.x, 0);
+    __syncthreads();
+    uint32_t it = 0;
+    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const int stage = it & 1;
+        if (threadIdx.x == 0 && tile + gridDim.x < tiles) issue(tile + gridDim.x, stage ^ 1);
+        const uint64_t p0 = tile * LOAD_PAIRS, p1 = min(p0 + (uint64_t)LOAD_PAIRS, ps.n_pairs);
+        const uint64_t p = p0 + threadIdx.x;
+        uint64_t oa0 = 0, oa1 = 0, ob0 = 0, ob1 = 0;
+        if (p < p1) oa0 = ps.a_offs[p], oa1 = ps.a_offs[p + 1], ob0 = ps.b_offs[p], ob1 = ps.b_offs[p + 1];
         {
-            const uint32_t s = mis_a + (uint32_t)(ps.a_offs[p] - a_lo), e = mis_a + (uint32_t)(ps.a_offs[p + 1] - a_lo);
-            for (uint32_t q = s >> 4; q < (e + 15u) >> 4; ++q)
-                acc += masked_sum16(s_a + 16u * q, (int)max(s, 16u * q) - (int)(16u * q), (int)min(e, 16u * q + 16u) - (int)(16u * q));
+            uint32_t done = 0;
+            const uint32_t parity = (it >> 1) & 1u;
+            while (!done)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(smem_u32(&mbar[stage])), "r"(parity) : "memory");
         }
-        {
-            const uint32_t s = mis_b + (uint32_t)(ps.b_offs[p] - b_lo), e = mis_b + (uint32_t)(ps.b_offs[p + 1] - b_lo);
-            for (uint32_t q = s >> 4; q < (e + 15u) >> 4; ++q)
-                acc += masked_sum16(s_b + 16u * q, (int)max(s, 16u * q) - (int)(16u * q), (int)min(e, 16u * q + 16u) - (int)(16u * q));
+        if (p < p1) {
+            const LoadTileMeta mt = meta[stage];
+            const uint8_t *s_a = lsm + (size_t)stage * stage_bytes, *s_b = s_a + cap_a;
+            uint32_t acc = 0;
+            {
+                const uint32_t s = mt.mis_a + (uint32_t)(oa0 - mt.a_lo), e = mt.mis_a + (uint32_t)(oa1 - mt.a_lo);
+                for (uint32_t q = s >> 4; q < (e + 15u) >> 4; ++q)
+                    acc += masked_sum16(s_a + 16u * q, (int)max(s, 16u * q) - (int)(16u * q), (int)min(e, 16u * q + 16u) - (int)(16u * q));
+            }
+            {
+                const uint32_t s = mt.mis_b + (uint32_t)(ob0 - mt.b_lo), e = mt.mis_b + (uint32_t)(ob1 - mt.b_lo);
+                for (uint32_t q = s >> 4; q < (e + 15u) >> 4; ++q)
+                    acc += masked_sum16(s_b + 16u * q, (int)max(s, 16u * q) - (int)(16u * q), (int)min(e, 16u * q + 16u) - (int)(16u * q));
+            }
+            ps.out[p] = acc;
         }
-        ps.out[p] = acc;
+        __syncthreads(); // stage `stage` may be refilled (and its meta rewritten) from the next iteration on
     }
 }
 

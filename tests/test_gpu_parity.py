@@ -273,3 +273,24 @@ def test_very_long_and_lopsided_pairs(scope, lev, oracle, algo):
     a2, b2 = BytesTape.from_strings([base, base[:2000], base]), BytesTape.from_strings([bytes(edits), bytes(edits), base[5:]])
     got = _check_pairs(lev, scope, oracle, a2, b2, algo)
     assert got[0] == 40 and got[2] == 5
+
+
+@pytest.mark.parametrize("gen", ["ascii64", "words", "utf8"])
+def test_load_phase_kernel_bytesums(scope, lev, gen):
+    """The pair-load-phase kernel (TMA bulk copies into shared memory) must deliver every byte of every pair:
+    its per-pair byte sums are checked against numpy."""
+    import torch
+    a, b = {"ascii64": lambda: datasets.ascii_pairs(70_001, 64), "words": lambda: datasets.words_pairs(5000),
+            "utf8": lambda: datasets.utf8_line_pairs(3000, 10, 200)}[gen]()
+    dev = torch.device("cuda", 0)
+    pad = lambda t: torch.cat([torch.from_numpy(t.data.copy()), torch.zeros(64, dtype=torch.uint8)]).to(dev)
+    ad, bd = pad(a), pad(b)
+    ao, bo = torch.from_numpy(a.offsets.view(np.int64).copy()).to(dev), torch.from_numpy(b.offsets.view(np.int64).copy()).to(dev)
+    out = torch.zeros(len(a), dtype=torch.int64, device=dev)
+    lev.load_phase_device(ad.data_ptr(), ao.data_ptr(), bd.data_ptr(), bo.data_ptr(), len(a), out.data_ptr(),
+                          stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    csa = np.concatenate([[0], np.cumsum(a.data.astype(np.int64))])
+    csb = np.concatenate([[0], np.cumsum(b.data.astype(np.int64))])
+    want = (csa[a.offsets[1:].astype(np.int64)] - csa[a.offsets[:-1].astype(np.int64)]) + (csb[b.offsets[1:].astype(np.int64)] - csb[b.offsets[:-1].astype(np.int64)])
+    assert np.array_equal(out.cpu().numpy(), want)
