@@ -113,6 +113,7 @@ struct swb_engine {
     AlignTables tables;
     std::vector<AlignTables *> d_tables; // per device
     const char *last_kernel = "none";
+    int spec_class = -1; // pattern class of the last uniform batch on the device-resident path (-1: do not speculate)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events; // pool
     std::vector<int> prof_device;                                  // device ordinal of each recorded pair
@@ -394,14 +395,14 @@ static inline uint32_t round16(uint32_t x) { return (x + 15u) & ~15u; }
 
 template <int K>
 static swb_status_t launch_bitpar(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count,
-                                  cudaStream_t stream, const char **err) {
+                                  cudaStream_t stream, const char **err, const uint32_t *verdict = nullptr, uint32_t verdict_seq = 0) {
     constexpr int T = BitparConfig<K>::THREADS;
     const size_t smem = (size_t)32 * T * K * sizeof(uint32_t);
     SWB_CUDA(allow_smem((const void *)lev_bitpar_kernel<K>, ctx.device, smem));
     const uint64_t blocks = (count + T - 1) / T;
     {
         ProfileBracket bracket(eng, ctx.device, stream);
-        lev_bitpar_kernel<K><<<(unsigned)blocks, T, smem, stream>>>(ps, begin, count);
+        lev_bitpar_kernel<K><<<(unsigned)blocks, T, smem, stream>>>(ps, begin, count, verdict, verdict_seq);
     }
     g_launches++;
     static const char *names[] = {"", "lev_bitpar<K=1>", "lev_bitpar<K=2>", "", "lev_bitpar<K=4>", "", "", "", "lev_bitpar<K=8>"};
@@ -540,12 +541,13 @@ static swb_status_t launch_class(swb_engine *eng, DeviceCtx &ctx, int dev_index,
 
 // Schedule counters for a device-resident PairSpace: enqueue the count kernel on `stream`; it publishes into
 // mapped host memory and re-arms the device counters itself (no memset / D2H copy / event on the critical path).
-static swb_status_t enqueue_schedule_count(DeviceCtx &ctx, const PairSpace &ps, cudaStream_t stream, const char **err) {
+static swb_status_t enqueue_schedule_count(DeviceCtx &ctx, const PairSpace &ps, cudaStream_t stream, const char **err,
+                                           int expected_class = -1) {
     const unsigned blocks = (unsigned)std::min<uint64_t>((ps.n_pairs + 255) / 256, (uint64_t)ctx.sm_count * 8);
     ctx.stats_seq++;
-    if (ctx.stats_seq == 0) ctx.stats_seq = 1;
+    if (ctx.stats_seq == 0 || ctx.stats_seq == 0xFFFFFFFFu) ctx.stats_seq = 1;
     ctx.stats_stream = stream;
-    schedule_count_kernel<<<blocks, 256, 0, stream>>>(ps, ctx.d_stats, ctx.h_stats_dev, ctx.stats_seq);
+    schedule_count_kernel<<<blocks, 256, 0, stream>>>(ps, ctx.d_stats, ctx.h_stats_dev, ctx.stats_seq, expected_class);
     g_launches++;
     SWB_CUDA(cudaGetLastError());
     return SWB_OK;
@@ -577,6 +579,7 @@ static swb_status_t wait_schedule_count(DeviceCtx &ctx, const char **err) {
 struct Plan {
     bool identity = true;        // single key: keep input order
     int n_classes = 0;
+    int cls[SCHED_MCLASSES];     // pattern-length class index of each entry
     uint64_t begin[SCHED_MCLASSES], count[SCHED_MCLASSES];
     uint32_t max_m[SCHED_MCLASSES], max_n[SCHED_MCLASSES];
 };
@@ -598,6 +601,7 @@ static Plan make_plan(ScheduleStats &st) {
         }
         if (class_count) {
             const int i = plan.n_classes++;
+            plan.cls[i] = c;
             plan.begin[i] = class_begin, plan.count[i] = class_count;
             plan.max_m[i] = st.max_m[c], plan.max_n[i] = st.max_n[c];
         }
@@ -614,10 +618,26 @@ static swb_status_t run_device_batch(swb_engine *eng, int dev_index, PairSpace p
     if (ps.n_pairs == 0) return SWB_OK;
     if (ps.n_pairs >= 0xFFFFFFFFull) return fail(err, SWB_INVALID_ARG, "more than 2^32-1 pairs in one call");
     ps.order = nullptr;
-    swb_status_t st = enqueue_schedule_count(ctx, ps, stream, err);
+    // Speculate that this batch has the shape of the previous one (thread-per-pair bit-vector classes only: their
+    // launch geometry depends on nothing but the pair count): the compute kernel is enqueued right behind the
+    // schedule kernel and gated by the on-device verdict, so the host round trip leaves the critical path.
+    const bool lev_bytes = (eng->kind == ENGINE_LEVENSHTEIN || eng->kind == ENGINE_LEVENSHTEIN_UTF8) && ps.len_shift == 0;
+    const int spec = (lev_bytes && eng->algorithm != SWB_ALGO_WAVEFRONT && eng->spec_class >= 0 && eng->spec_class <= 3) ? eng->spec_class : -1;
+    swb_status_t st = enqueue_schedule_count(ctx, ps, stream, err, spec);
     if (st != SWB_OK) return st;
+    if (spec >= 0) {
+        const uint32_t *verdict = &ctx.d_stats->verdict;
+        if (spec == 0) st = launch_bitpar<1>(eng, ctx, ps, 0, ps.n_pairs, stream, err, verdict, ctx.stats_seq);
+        else if (spec == 1) st = launch_bitpar<2>(eng, ctx, ps, 0, ps.n_pairs, stream, err, verdict, ctx.stats_seq);
+        else if (spec == 2) st = launch_bitpar<4>(eng, ctx, ps, 0, ps.n_pairs, stream, err, verdict, ctx.stats_seq);
+        else st = launch_bitpar<8>(eng, ctx, ps, 0, ps.n_pairs, stream, err, verdict, ctx.stats_seq);
+        if (st != SWB_OK) return st;
+    }
     if ((st = wait_schedule_count(ctx, err)) != SWB_OK) return st;
     Plan plan = make_plan(*ctx.h_stats);
+    const bool uniform = plan.identity && plan.n_classes == 1;
+    eng->spec_class = (uniform && lev_bytes) ? plan.cls[0] : -1;
+    if (spec >= 0 && uniform && plan.cls[0] == spec) return SWB_OK; // the bet held: the gated kernel is doing the work
     if (!plan.identity) {
         SWB_CUDA(ctx.order.reserve(ps.n_pairs * sizeof(uint32_t)));
         SWB_CUDA(cudaMemcpyAsync(ctx.d_stats->cursor, ctx.h_stats->cursor, sizeof(ctx.h_stats->cursor), cudaMemcpyHostToDevice, stream));

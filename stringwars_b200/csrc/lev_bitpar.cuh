@@ -61,9 +61,12 @@ __device__ __forceinline__ void load_words(const unsigned char *entry, int tid, 
     }
 }
 
+// `verdict` (optional): speculative launch — run only if *verdict == verdict_seq (see schedule.cuh).
 template <int K>
-__global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(PairSpace ps, uint64_t begin, uint64_t count) {
+__global__ void __launch_bounds__(BitparConfig<K>::THREADS)
+    lev_bitpar_kernel(PairSpace ps, uint64_t begin, uint64_t count, const uint32_t *verdict, uint32_t verdict_seq) {
     constexpr int T = BitparConfig<K>::THREADS;
+    if (verdict != nullptr && *reinterpret_cast<const volatile uint32_t *>(verdict) != verdict_seq) return;
     constexpr uint32_t ESTRIDE = T * K * 4; // bytes between consecutive table entries
     extern __shared__ __align__(16) unsigned char tbl_bytes[]; // [32 entries][T][K] u32
     const int tid = threadIdx.x;
