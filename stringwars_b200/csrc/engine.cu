@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <set>
 #include <utility>
@@ -144,14 +145,17 @@ struct ProfileBracket {
 };
 
 static std::mutex g_attr_mutex;
-static std::set<std::pair<const void *, int>> g_attr_done;
+static std::map<std::pair<const void *, int>, size_t> g_attr_done;
 
+// Opt a kernel in to `bytes` of dynamic shared memory (> 48 KB needs the attribute). The attribute is raised to
+// exactly what has been asked for so far: kernels with static shared memory cannot take the full 227 KB.
 static cudaError_t allow_smem(const void *func, int device, size_t bytes) {
     if (bytes <= 48 * 1024) return cudaSuccess;
     std::lock_guard<std::mutex> lock(g_attr_mutex);
-    if (g_attr_done.count({func, device})) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) g_attr_done.insert({func, device});
+    auto it = g_attr_done.find({func, device});
+    if (it != g_attr_done.end() && it->second >= bytes) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) g_attr_done[{func, device}] = bytes;
     return e;
 }
 
