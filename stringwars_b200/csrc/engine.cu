@@ -86,6 +86,8 @@ struct DeviceCtx {
     int sm_count = 0;
     int max_smem_optin = 0;
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+    cudaStream_t side_stream = nullptr; // schedule kernel of speculative device-resident calls
+    cudaEvent_t ev_inputs = nullptr;    // "caller's stream has reached this call": inputs are ready
     ScheduleStats *d_stats = nullptr;
     ScheduleStats *h_stats = nullptr;     // pinned + mapped: the schedule kernel publishes into it directly
     ScheduleStats *h_stats_dev = nullptr; // device alias of h_stats
@@ -187,6 +189,8 @@ static void destroy_ctx(DeviceCtx &c) {
     cudaSetDevice(c.device);
     if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
     if (c.compute_stream) cudaStreamDestroy(c.compute_stream);
+    if (c.side_stream) cudaStreamDestroy(c.side_stream);
+    if (c.ev_inputs) cudaEventDestroy(c.ev_inputs);
     if (c.d_stats) cudaFree(c.d_stats);
     if (c.h_stats) cudaFreeHost(c.h_stats);
     if (c.ev_offsets) cudaEventDestroy(c.ev_offsets);
@@ -213,6 +217,8 @@ extern "C" swb_status_t swb_scope_create(int first_device, int num_devices, swb_
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c.compute_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c.side_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c.ev_inputs, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc(&c.d_stats, sizeof(ScheduleStats));
         if (e == cudaSuccess) e = cudaMemset(c.d_stats, 0, sizeof(ScheduleStats));
         if (e == cudaSuccess) e = cudaMemset(&c.d_stats->min_m, 0xFF, 2 * sizeof(uint32_t));
@@ -399,14 +405,14 @@ static inline uint32_t round16(uint32_t x) { return (x + 15u) & ~15u; }
 
 template <int K>
 static swb_status_t launch_bitpar(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count,
-                                  cudaStream_t stream, const char **err, const uint32_t *verdict = nullptr, uint32_t verdict_seq = 0) {
+                                  cudaStream_t stream, const char **err) {
     constexpr int T = BitparConfig<K>::THREADS;
     const size_t smem = (size_t)32 * T * K * sizeof(uint32_t);
     SWB_CUDA(allow_smem((const void *)lev_bitpar_kernel<K>, ctx.device, smem));
     const uint64_t blocks = (count + T - 1) / T;
     {
         ProfileBracket bracket(eng, ctx.device, stream);
-        lev_bitpar_kernel<K><<<(unsigned)blocks, T, smem, stream>>>(ps, begin, count, verdict, verdict_seq);
+        lev_bitpar_kernel<K><<<(unsigned)blocks, T, smem, stream>>>(ps, begin, count);
     }
     g_launches++;
     static const char *names[] = {"", "lev_bitpar<K=1>", "lev_bitpar<K=2>", "", "lev_bitpar<K=4>", "", "", "", "lev_bitpar<K=8>"};
@@ -545,13 +551,12 @@ static swb_status_t launch_class(swb_engine *eng, DeviceCtx &ctx, int dev_index,
 
 // Schedule counters for a device-resident PairSpace: enqueue the count kernel on `stream`; it publishes into
 // mapped host memory and re-arms the device counters itself (no memset / D2H copy / event on the critical path).
-static swb_status_t enqueue_schedule_count(DeviceCtx &ctx, const PairSpace &ps, cudaStream_t stream, const char **err,
-                                           int expected_class = -1) {
-    const unsigned blocks = (unsigned)std::min<uint64_t>((ps.n_pairs + 255) / 256, (uint64_t)ctx.sm_count * 8);
+static swb_status_t enqueue_schedule_count(DeviceCtx &ctx, const PairSpace &ps, cudaStream_t stream, const char **err) {
+    const unsigned blocks = (unsigned)std::min<uint64_t>((ps.n_pairs + 1023) / 1024, (uint64_t)ctx.sm_count * 4);
     ctx.stats_seq++;
     if (ctx.stats_seq == 0 || ctx.stats_seq == 0xFFFFFFFFu) ctx.stats_seq = 1;
     ctx.stats_stream = stream;
-    schedule_count_kernel<<<blocks, 256, 0, stream>>>(ps, ctx.d_stats, ctx.h_stats_dev, ctx.stats_seq, expected_class);
+    schedule_count_kernel<<<blocks, 256, 0, stream>>>(ps, ctx.d_stats, ctx.h_stats_dev, ctx.stats_seq);
     g_launches++;
     SWB_CUDA(cudaGetLastError());
     return SWB_OK;
@@ -622,26 +627,31 @@ static swb_status_t run_device_batch(swb_engine *eng, int dev_index, PairSpace p
     if (ps.n_pairs == 0) return SWB_OK;
     if (ps.n_pairs >= 0xFFFFFFFFull) return fail(err, SWB_INVALID_ARG, "more than 2^32-1 pairs in one call");
     ps.order = nullptr;
-    // Speculate that this batch has the shape of the previous one (thread-per-pair bit-vector classes only: their
-    // launch geometry depends on nothing but the pair count): the compute kernel is enqueued right behind the
-    // schedule kernel and gated by the on-device verdict, so the host round trip leaves the critical path.
+    // Speculate that this batch has the shape of the previous one. A thread-per-pair bit-vector kernel is correct
+    // for every pair that fits its K words and skips the others, and its launch geometry depends on nothing but
+    // the pair count, so it goes onto the caller's stream IMMEDIATELY while the schedule kernel runs beside it on
+    // a side stream: the host round trip and the schedule kernel leave the critical path. If the counters then
+    // show a different shape, the batch is simply processed again the regular way (results overwritten in order).
     const bool lev_bytes = (eng->kind == ENGINE_LEVENSHTEIN || eng->kind == ENGINE_LEVENSHTEIN_UTF8) && ps.len_shift == 0;
     const int spec = (lev_bytes && eng->algorithm != SWB_ALGO_WAVEFRONT && eng->spec_class >= 0 && eng->spec_class <= 3) ? eng->spec_class : -1;
-    swb_status_t st = enqueue_schedule_count(ctx, ps, stream, err, spec);
-    if (st != SWB_OK) return st;
+    swb_status_t st;
     if (spec >= 0) {
-        const uint32_t *verdict = &ctx.d_stats->verdict;
-        if (spec == 0) st = launch_bitpar<1>(eng, ctx, ps, 0, ps.n_pairs, stream, err, verdict, ctx.stats_seq);
-        else if (spec == 1) st = launch_bitpar<2>(eng, ctx, ps, 0, ps.n_pairs, stream, err, verdict, ctx.stats_seq);
-        else if (spec == 2) st = launch_bitpar<4>(eng, ctx, ps, 0, ps.n_pairs, stream, err, verdict, ctx.stats_seq);
-        else st = launch_bitpar<8>(eng, ctx, ps, 0, ps.n_pairs, stream, err, verdict, ctx.stats_seq);
+        SWB_CUDA(cudaEventRecord(ctx.ev_inputs, stream));
+        SWB_CUDA(cudaStreamWaitEvent(ctx.side_stream, ctx.ev_inputs, 0));
+        if (spec == 0) st = launch_bitpar<1>(eng, ctx, ps, 0, ps.n_pairs, stream, err);
+        else if (spec == 1) st = launch_bitpar<2>(eng, ctx, ps, 0, ps.n_pairs, stream, err);
+        else if (spec == 2) st = launch_bitpar<4>(eng, ctx, ps, 0, ps.n_pairs, stream, err);
+        else st = launch_bitpar<8>(eng, ctx, ps, 0, ps.n_pairs, stream, err);
         if (st != SWB_OK) return st;
+        if ((st = enqueue_schedule_count(ctx, ps, ctx.side_stream, err)) != SWB_OK) return st;
+    } else if ((st = enqueue_schedule_count(ctx, ps, stream, err)) != SWB_OK) {
+        return st;
     }
     if ((st = wait_schedule_count(ctx, err)) != SWB_OK) return st;
     Plan plan = make_plan(*ctx.h_stats);
     const bool uniform = plan.identity && plan.n_classes == 1;
     eng->spec_class = (uniform && lev_bytes) ? plan.cls[0] : -1;
-    if (spec >= 0 && uniform && plan.cls[0] == spec) return SWB_OK; // the bet held: the gated kernel is doing the work
+    if (spec >= 0 && uniform && plan.cls[0] == spec) return SWB_OK; // the bet held: that kernel is the batch
     if (!plan.identity) {
         SWB_CUDA(ctx.order.reserve(ps.n_pairs * sizeof(uint32_t)));
         SWB_CUDA(cudaMemcpyAsync(ctx.d_stats->cursor, ctx.h_stats->cursor, sizeof(ctx.h_stats->cursor), cudaMemcpyHostToDevice, stream));
@@ -781,17 +791,29 @@ extern "C" swb_status_t swb_load_phase_device(swb_engine_t *engine, int device_i
     if ((st = wait_schedule_count(ctx, err)) != SWB_OK) return st;
     uint32_t max_len = 0;
     for (int c = 0; c < SCHED_MCLASSES; ++c) max_len = std::max(max_len, ctx.h_stats->max_n[c]);
-    const uint32_t cap = (round16((uint32_t)LOAD_PAIRS * max_len + 32u) + 127u) & ~127u;
-    const size_t smem = 4 * (size_t)cap; // two stages x (a span + b span)
-    if (smem > (size_t)ctx.max_smem_optin) return fail(err, SWB_TOO_LONG, "load-phase kernel supports strings up to %d bytes", ctx.max_smem_optin / (4 * LOAD_PAIRS));
-    SWB_CUDA(allow_smem((const void *)load_phase_kernel, ctx.device, smem));
-    {
+    // SWB_LOAD_VARIANT: 0 = persistent CTAs with a two-stage TMA pipeline, 1 = one tile per CTA (default: see DESIGN.md)
+    static const int variant = getenv("SWB_LOAD_VARIANT") ? atoi(getenv("SWB_LOAD_VARIANT")) : 0;
+    static const uint32_t tile_override = getenv("SWB_LOAD_TILE") ? (uint32_t)atoi(getenv("SWB_LOAD_TILE")) : 0u;
+    const uint32_t stages = variant == 0 ? 2u : 1u;
+    // pairs per tile: as many as the threads of a block (256) unless the staged spans overflow shared memory
+    const uint32_t budget = (uint32_t)(ctx.max_smem_optin - 1024) / (2u * stages);
+    uint32_t tile_pairs = tile_override ? std::min<uint32_t>(tile_override, LOAD_PAIRS) : (uint32_t)LOAD_PAIRS;
+    while (tile_pairs > 1 && tile_pairs * max_len + 160u > budget) tile_pairs /= 2;
+    const uint32_t cap = (round16(tile_pairs * max_len + 32u) + 127u) & ~127u;
+    const size_t smem = 2 * stages * (size_t)cap;
+    if (smem > (size_t)ctx.max_smem_optin - 1024) return fail(err, SWB_TOO_LONG, "load-phase kernel supports strings up to %u bytes", budget - 160u);
+    const uint64_t tiles = (n_pairs + tile_pairs - 1) / tile_pairs;
+    if (variant == 0) {
+        SWB_CUDA(allow_smem((const void *)load_phase_kernel, ctx.device, smem));
         // persistent grid: as many CTAs as fit (shared memory bound), never more than there are tiles
-        const uint64_t tiles = (n_pairs + LOAD_PAIRS - 1) / LOAD_PAIRS;
         const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (size_t)(ctx.max_smem_optin - 1024) / (smem + 1024)));
         const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)ctx.sm_count * per_sm);
         ProfileBracket bracket(engine, ctx.device, stream);
-        load_phase_kernel<<<grid, LOAD_THREADS, smem, stream>>>(ps, cap, cap);
+        load_phase_kernel<<<grid, LOAD_THREADS, smem, stream>>>(ps, cap, cap, tile_pairs);
+    } else {
+        SWB_CUDA(allow_smem((const void *)load_phase_simple_kernel, ctx.device, smem));
+        ProfileBracket bracket(engine, ctx.device, stream);
+        load_phase_simple_kernel<<<(unsigned)tiles, LOAD_THREADS, smem, stream>>>(ps, cap, cap, tile_pairs);
     }
     g_launches++;
     engine->last_kernel = "load_phase";

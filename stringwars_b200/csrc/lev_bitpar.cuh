@@ -61,12 +61,12 @@ __device__ __forceinline__ void load_words(const unsigned char *entry, int tid, 
     }
 }
 
-// `verdict` (optional): speculative launch — run only if *verdict == verdict_seq (see schedule.cuh).
+// A thread computes any pair whose pattern fits its K words and SKIPS (writes nothing for) a longer one: that is
+// what lets the host launch this kernel speculatively, before the batch's length statistics are known — the
+// statistics then tell the host whether anything was skipped (engine.cu, run_device_batch).
 template <int K>
-__global__ void __launch_bounds__(BitparConfig<K>::THREADS)
-    lev_bitpar_kernel(PairSpace ps, uint64_t begin, uint64_t count, const uint32_t *verdict, uint32_t verdict_seq) {
+__global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(PairSpace ps, uint64_t begin, uint64_t count) {
     constexpr int T = BitparConfig<K>::THREADS;
-    if (verdict != nullptr && *reinterpret_cast<const volatile uint32_t *>(verdict) != verdict_seq) return;
     constexpr uint32_t ESTRIDE = T * K * 4; // bytes between consecutive table entries
     extern __shared__ __align__(16) unsigned char tbl_bytes[]; // [32 entries][T][K] u32
     const int tid = threadIdx.x;
@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS)
         ps.out[pv.out_index] = n;
         return;
     }
+    if (m > 32u * K) return; // not this kernel's class (speculative launch on a batch that changed shape)
     const uint32_t s = 32u * K - m; // pattern symbol i lives at bit position s + i
 
     // ---- build the nibble tables: bit p of HI[h] (LO[l]) is set iff the symbol at position p has high (low) nibble h (l)

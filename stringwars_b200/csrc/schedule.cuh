@@ -22,7 +22,6 @@ struct ScheduleStats {
     uint32_t min_m, min_n;
     uint32_t ticket;  // blocks that have merged their counters (device copy only)
     uint32_t seq;     // host copy only: sequence number of the call whose counters are complete
-    uint32_t verdict; // device copy only: == seq of the call iff the batch matched the speculated plan
 };
 
 __device__ __forceinline__ int mclass_of(uint32_t m) {
@@ -39,18 +38,11 @@ __device__ __forceinline__ int key_of(uint32_t m, uint32_t n) {
 // `stats` (device) must be all-zero with min_* = 0xFFFFFFFF on entry; the LAST block to finish publishes the
 // merged counters into `published` (mapped, page-locked host memory: no D2H copy, no event — the host polls
 // `published->seq`) and restores `stats` to its entry state for the next call.
-//
-// Speculation: the host may enqueue the compute kernel right behind this one, betting that the batch looks like
-// the previous one (one pattern class `expected_class`, at most two text-length bins, identity order). The last
-// block checks that bet against the merged counters and leaves `stats->verdict = seq` if it holds; the
-// speculatively launched kernel reads the verdict on entry and returns without touching memory otherwise.
-__global__ void __launch_bounds__(256) schedule_count_kernel(PairSpace ps, ScheduleStats *stats, ScheduleStats *published, uint32_t seq,
-                                                             int expected_class) {
+__global__ void __launch_bounds__(256) schedule_count_kernel(PairSpace ps, ScheduleStats *stats, ScheduleStats *published, uint32_t seq) {
     __shared__ uint32_t s_counts[SCHED_KEYS];
     __shared__ uint32_t s_max_m[SCHED_MCLASSES], s_max_n[SCHED_MCLASSES];
     __shared__ uint32_t s_min_m, s_min_n;
     __shared__ bool s_last;
-    __shared__ uint32_t s_nonempty, s_class_mask;
     for (int i = threadIdx.x; i < SCHED_KEYS; i += blockDim.x) s_counts[i] = 0;
     if (threadIdx.x < SCHED_MCLASSES) s_max_m[threadIdx.x] = 0, s_max_n[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_min_m = 0xFFFFFFFFu, s_min_n = 0xFFFFFFFFu;
@@ -98,8 +90,8 @@ __global__ void __launch_bounds__(256) schedule_count_kernel(PairSpace ps, Sched
     for (int i = threadIdx.x; i < SCHED_KEYS; i += blockDim.x)
         if (s_counts[i]) atomicAdd(&stats->counts[i], s_counts[i]);
     if (threadIdx.x < SCHED_MCLASSES) {
-        atomicMax(&stats->max_m[threadIdx.x], s_max_m[threadIdx.x]);
-        atomicMax(&stats->max_n[threadIdx.x], s_max_n[threadIdx.x]);
+        if (s_max_m[threadIdx.x]) atomicMax(&stats->max_m[threadIdx.x], s_max_m[threadIdx.x]);
+        if (s_max_n[threadIdx.x]) atomicMax(&stats->max_n[threadIdx.x], s_max_n[threadIdx.x]);
     }
     if (threadIdx.x == 0) {
         atomicMin(&stats->min_m, s_min_m);
@@ -112,21 +104,9 @@ __global__ void __launch_bounds__(256) schedule_count_kernel(PairSpace ps, Sched
     if (!s_last) return;
     __threadfence();
     volatile ScheduleStats *vs = stats;
-    if (threadIdx.x == 0) s_nonempty = 0, s_class_mask = 0;
-    __syncthreads();
     for (int i = threadIdx.x; i < SCHED_KEYS; i += blockDim.x) {
-        const uint32_t c = vs->counts[i];
-        published->counts[i] = c;
+        published->counts[i] = vs->counts[i];
         stats->counts[i] = 0;
-        if (c) {
-            atomicAdd(&s_nonempty, 1u);
-            atomicOr(&s_class_mask, 1u << (i / SCHED_NBINS));
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const bool holds = expected_class >= 0 && s_class_mask == (1u << expected_class) && s_nonempty <= 2u;
-        stats->verdict = holds ? seq : ~seq;
     }
     if (threadIdx.x < SCHED_MCLASSES) {
         published->max_m[threadIdx.x] = vs->max_m[threadIdx.x];
@@ -196,19 +176,19 @@ struct LoadTileMeta {
 // Persistent CTAs, two shared-memory stages: while the threads byte-sum tile i out of stage i&1, the TMA engine
 // is already filling stage (i+1)&1 with tile i+gridDim.x. Per-pair offsets are fetched before waiting on the
 // mbarrier so their latency hides behind the bulk copy.
-__global__ void __launch_bounds__(LOAD_THREADS) load_phase_kernel(PairSpace ps, uint32_t cap_a, uint32_t cap_b) {
+__global__ void __launch_bounds__(LOAD_THREADS) load_phase_kernel(PairSpace ps, uint32_t cap_a, uint32_t cap_b, uint32_t tile_pairs) {
     extern __shared__ __align__(128) uint8_t lsm[];
     __shared__ __align__(8) uint64_t mbar[2];
     __shared__ LoadTileMeta meta[2];
     const uint32_t stage_bytes = cap_a + cap_b;
-    const uint64_t tiles = (ps.n_pairs + LOAD_PAIRS - 1) / LOAD_PAIRS;
+    const uint64_t tiles = (ps.n_pairs + tile_pairs - 1) / tile_pairs; // tile_pairs <= LOAD_THREADS pairs per tile
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[0])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[1])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     auto issue = [&](uint64_t tile, int stage) { // thread 0 only
-        const uint64_t p0 = tile * LOAD_PAIRS, p1 = min(p0 + (uint64_t)LOAD_PAIRS, ps.n_pairs);
+        const uint64_t p0 = tile * tile_pairs, p1 = min(p0 + (uint64_t)tile_pairs, ps.n_pairs);
         const uint64_t a_lo = ps.a_offs[p0], a_hi = ps.a_offs[p1], b_lo = ps.b_offs[p0], b_hi = ps.b_offs[p1];
         const uint8_t *ga = ps.a_data + a_lo, *gb = ps.b_data + b_lo;
         const uint32_t mis_a = (uint32_t)(reinterpret_cast<uintptr_t>(ga) & 15u), mis_b = (uint32_t)(reinterpret_cast<uintptr_t>(gb) & 15u);
@@ -228,7 +208,7 @@ __global__ void __launch_bounds__(LOAD_THREADS) load_phase_kernel(PairSpace ps, 
     for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
         const int stage = it & 1;
         if (threadIdx.x == 0 && tile + gridDim.x < tiles) issue(tile + gridDim.x, stage ^ 1);
-        const uint64_t p0 = tile * LOAD_PAIRS, p1 = min(p0 + (uint64_t)LOAD_PAIRS, ps.n_pairs);
+        const uint64_t p0 = tile * tile_pairs, p1 = min(p0 + (uint64_t)tile_pairs, ps.n_pairs);
         const uint64_t p = p0 + threadIdx.x;
         uint64_t oa0 = 0, oa1 = 0, ob0 = 0, ob1 = 0;
         if (p < p1) oa0 = ps.a_offs[p], oa1 = ps.a_offs[p + 1], ob0 = ps.b_offs[p], ob1 = ps.b_offs[p + 1];
@@ -256,6 +236,51 @@ __global__ void __launch_bounds__(LOAD_THREADS) load_phase_kernel(PairSpace ps, 
             ps.out[p] = acc;
         }
         __syncthreads(); // stage `stage` may be refilled (and its meta rewritten) from the next iteration on
+    }
+}
+
+// Variant with one tile per CTA (no persistence, single stage): latency is hidden by CTA-level parallelism
+// instead of a software pipeline. Selected with SWB_LOAD_VARIANT=1 for A/B measurements.
+__global__ void __launch_bounds__(LOAD_THREADS) load_phase_simple_kernel(PairSpace ps, uint32_t cap_a, uint32_t cap_b, uint32_t tile_pairs) {
+    extern __shared__ __align__(128) uint8_t lsm[];
+    __shared__ __align__(8) uint64_t mbar;
+    uint8_t *s_a = lsm, *s_b = lsm + cap_a;
+    const uint64_t p0 = (uint64_t)blockIdx.x * tile_pairs;
+    const uint64_t p1 = min(p0 + (uint64_t)tile_pairs, ps.n_pairs);
+    const uint64_t a_lo = ps.a_offs[p0], a_hi = ps.a_offs[p1], b_lo = ps.b_offs[p0], b_hi = ps.b_offs[p1];
+    const uint8_t *ga = ps.a_data + a_lo, *gb = ps.b_data + b_lo;
+    const uint32_t mis_a = (uint32_t)(reinterpret_cast<uintptr_t>(ga) & 15u), mis_b = (uint32_t)(reinterpret_cast<uintptr_t>(gb) & 15u);
+    const uint32_t bytes_a = a_hi > a_lo ? ((mis_a + (uint32_t)(a_hi - a_lo) + 15u) & ~15u) : 0u;
+    const uint32_t bytes_b = b_hi > b_lo ? ((mis_b + (uint32_t)(b_hi - b_lo) + 15u) & ~15u) : 0u;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes_a + bytes_b) : "memory");
+        if (bytes_a) bulk_g2s(s_a, ga - mis_a, bytes_a, &mbar);
+        if (bytes_b) bulk_g2s(s_b, gb - mis_b, bytes_b, &mbar);
+    }
+    const uint64_t p = p0 + threadIdx.x;
+    uint64_t oa0 = 0, oa1 = 0, ob0 = 0, ob1 = 0;
+    if (p < p1) oa0 = ps.a_offs[p], oa1 = ps.a_offs[p + 1], ob0 = ps.b_offs[p], ob1 = ps.b_offs[p + 1];
+    __syncthreads(); // mbarrier init visible to every thread before anyone waits on it
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
+    }
+    if (p < p1) {
+        uint32_t acc = 0;
+        {
+            const uint32_t s = mis_a + (uint32_t)(oa0 - a_lo), e = mis_a + (uint32_t)(oa1 - a_lo);
+            for (uint32_t q = s >> 4; q < (e + 15u) >> 4; ++q)
+                acc += masked_sum16(s_a + 16u * q, (int)max(s, 16u * q) - (int)(16u * q), (int)min(e, 16u * q + 16u) - (int)(16u * q));
+        }
+        {
+            const uint32_t s = mis_b + (uint32_t)(ob0 - b_lo), e = mis_b + (uint32_t)(ob1 - b_lo);
+            for (uint32_t q = s >> 4; q < (e + 15u) >> 4; ++q)
+                acc += masked_sum16(s_b + 16u * q, (int)max(s, 16u * q) - (int)(16u * q), (int)min(e, 16u * q + 16u) - (int)(16u * q));
+        }
+        ps.out[p] = acc;
     }
 }
 
