@@ -217,7 +217,13 @@ extern "C" swb_status_t swb_scope_create(int first_device, int num_devices, swb_
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c.compute_stream, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c.side_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) {
+            // highest priority: the (tiny) schedule kernel must get SM slots while a compute kernel launched just
+            // before it on another stream still has blocks waiting, otherwise it only runs in that kernel's tail
+            int least = 0, greatest = 0;
+            cudaDeviceGetStreamPriorityRange(&least, &greatest);
+            e = cudaStreamCreateWithPriority(&c.side_stream, cudaStreamNonBlocking, greatest);
+        }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c.ev_inputs, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc(&c.d_stats, sizeof(ScheduleStats));
         if (e == cudaSuccess) e = cudaMemset(c.d_stats, 0, sizeof(ScheduleStats));
@@ -791,8 +797,9 @@ extern "C" swb_status_t swb_load_phase_device(swb_engine_t *engine, int device_i
     if ((st = wait_schedule_count(ctx, err)) != SWB_OK) return st;
     uint32_t max_len = 0;
     for (int c = 0; c < SCHED_MCLASSES; ++c) max_len = std::max(max_len, ctx.h_stats->max_n[c]);
-    // SWB_LOAD_VARIANT: 0 = persistent CTAs with a two-stage TMA pipeline, 1 = one tile per CTA (default: see DESIGN.md)
-    static const int variant = getenv("SWB_LOAD_VARIANT") ? atoi(getenv("SWB_LOAD_VARIANT")) : 0;
+    // SWB_LOAD_VARIANT: 1 = one tile per CTA (default; measured faster, profiles/README.md), 0 = persistent CTAs with a
+    // two-stage TMA pipeline
+    static const int variant = getenv("SWB_LOAD_VARIANT") ? atoi(getenv("SWB_LOAD_VARIANT")) : 1;
     static const uint32_t tile_override = getenv("SWB_LOAD_TILE") ? (uint32_t)atoi(getenv("SWB_LOAD_TILE")) : 0u;
     const uint32_t stages = variant == 0 ? 2u : 1u;
     // pairs per tile: as many as the threads of a block (256) unless the staged spans overflow shared memory
