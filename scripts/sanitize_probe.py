@@ -1,0 +1,69 @@
+"""Small run through every kernel family, meant to be executed under compute-sanitizer (memcheck / racecheck).
+Exits non-zero on any mismatch against the CPU oracle."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import stringwars_b200 as sw
+from stringwars_b200 import datasets
+from stringwars_b200.tape import BytesTape
+from oracle import oracle as orc
+
+scope = sw.DeviceScope.gpu_device(0)
+lev = sw.LevenshteinDistances(scope)
+rng = np.random.default_rng(1)
+alpha = np.frombuffer(b"ACGT", np.uint8)
+ok = True
+
+def check(name, got, want):
+    global ok
+    good = np.array_equal(got, want)
+    ok &= good
+    print(f"{name}: {'ok' if good else 'MISMATCH'} ({lev.last_kernel})", flush=True)
+
+cases = {
+    "bitpar K=1 ragged": datasets.words_pairs(300),
+    "bitpar K=2": datasets.ascii_pairs(300, 64),
+    "bitpar K=4 misaligned": (datasets._ragged(rng.integers(65, 129, 200), alpha, rng, False), datasets._ragged(rng.integers(65, 300, 200), alpha, rng, False)),
+    "bitpar K=8": datasets.ascii_pairs(100, 256),
+    "coop G=8": datasets.ascii_pairs(40, 500),
+    "coop G=16": datasets.acgt_pairs(24, 1024),
+    "coop G=32 K=2/4 + strips": (datasets._ragged(np.array([2048, 3000, 4096, 4500, 5]), alpha, rng, False), datasets._ragged(np.array([2048, 3100, 4096, 4600, 4800]), alpha, rng, False)),
+    "mixed (bucketed)": datasets.utf8_line_pairs(300, 10, 400),
+}
+for name, (a, b) in cases.items():
+    want = orc.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, orc.RAPIDFUZZ_CLASS, threads=4)
+    check(name, lev.compute_pairs(scope, a, b), want)
+    lev.set_algorithm(sw.ALGO_WAVEFRONT)
+    check(name + " [wavefront]", lev.compute_pairs(scope, a, b), want)
+    lev.set_algorithm(sw.ALGO_AUTO)
+u8 = sw.LevenshteinDistancesUtf8(scope)
+a, b = datasets.utf8_line_pairs(200, 10, 300)
+check("utf8 engine", u8.compute_pairs(scope, a, b), orc.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, orc.UTF8, threads=4))
+btc, costs = sw.unary_class_costs(2, -1)
+a, b = datasets.acgt_pairs(30, 700)
+for cls, local in ((sw.NeedlemanWunschScores, False), (sw.SmithWatermanScores, True)):
+    for o, e in ((-2, -2), (-5, -1)):
+        eng = cls(scope, btc, costs, o, e)
+        got = eng.compute_pairs(scope, a, b)
+        want = orc.align_pairs(a.data, a.offsets, b.data, b.offsets, btc, costs, o, e, 0, local, threads=4)
+        ok &= np.array_equal(got, want)
+        print(f"{cls.__name__} ({o},{e}): {'ok' if np.array_equal(got, want) else 'MISMATCH'} ({eng.last_kernel})", flush=True)
+q = datasets.words_pairs(80)[0]
+check("cross", lev.compute(scope, q.subview(0, 40), q.subview(40, 80)), orc.levenshtein_cross(q.data, q.offsets[:41], q.data, q.offsets[40:81]))
+import torch
+dev = torch.device("cuda", 0)
+a, b = datasets.ascii_pairs(1000, 64)
+pad = lambda t: torch.cat([torch.from_numpy(t.data.copy()), torch.zeros(64, dtype=torch.uint8)]).to(dev)
+ad, bd = pad(a), pad(b)
+ao, bo = torch.from_numpy(a.offsets.view(np.int64).copy()).to(dev), torch.from_numpy(b.offsets.view(np.int64).copy()).to(dev)
+out = torch.zeros(1000, dtype=torch.int64, device=dev)
+lev.load_phase_device(ad.data_ptr(), ao.data_ptr(), bd.data_ptr(), bo.data_ptr(), 1000, out.data_ptr())
+torch.cuda.synchronize()
+want = a.data.reshape(1000, 64).astype(np.int64).sum(1) + b.data.reshape(1000, 64).astype(np.int64).sum(1)
+ok &= np.array_equal(out.cpu().numpy(), want)
+print("load_phase:", "ok" if np.array_equal(out.cpu().numpy(), want) else "MISMATCH", flush=True)
+for _ in range(3):  # speculative path (second and third device-resident calls of the same shape)
+    lev.compute_pairs_device(ad.data_ptr(), ao.data_ptr(), bd.data_ptr(), bo.data_ptr(), 1000, out.data_ptr())
+torch.cuda.synchronize()
+check("device-resident speculative", out.cpu().numpy().view(np.uint64), orc.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets))
+sys.exit(0 if ok else 1)
