@@ -30,6 +30,9 @@ cases = {
     "coop G=32 K=2/4 + strips": (datasets._ragged(np.array([2048, 3000, 4096, 4500, 5]), alpha, rng, False), datasets._ragged(np.array([2048, 3100, 4096, 4600, 4800]), alpha, rng, False)),
     "mixed (bucketed)": datasets.utf8_line_pairs(300, 10, 400),
 }
+long_cases = {"coop strips + chunks": (datasets._ragged(np.array([9000, 4097, 30]), alpha, rng, False), datasets._ragged(np.array([9500, 5000, 40000]), alpha, rng, False))}
+for name, (a, b) in long_cases.items():
+    check(name, lev.compute_pairs(scope, a, b), orc.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, orc.RAPIDFUZZ_CLASS, threads=4))
 for name, (a, b) in cases.items():
     want = orc.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, orc.RAPIDFUZZ_CLASS, threads=4)
     check(name, lev.compute_pairs(scope, a, b), want)

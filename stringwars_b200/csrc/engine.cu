@@ -97,6 +97,7 @@ struct DeviceCtx {
     std::vector<cudaEvent_t> ev_chunks;
     DeviceBuffer order, a_data, a_offs, b_data, b_offs, out;
     DeviceBuffer sym_a, sym_a_offs, sym_b, sym_b_offs, scan_tmp, flags; // UTF-8 engine scratch
+    DeviceBuffer hscratch; // per-column delta bits between row strips of the lane-group bit-vector kernel
 };
 
 struct swb_scope {
@@ -196,7 +197,7 @@ static void destroy_ctx(DeviceCtx &c) {
     if (c.ev_offsets) cudaEventDestroy(c.ev_offsets);
     for (auto e : c.ev_chunks) cudaEventDestroy(e);
     c.order.release(), c.a_data.release(), c.a_offs.release(), c.b_data.release(), c.b_offs.release(), c.out.release();
-    c.sym_a.release(), c.sym_a_offs.release(), c.sym_b.release(), c.sym_b_offs.release(), c.scan_tmp.release(), c.flags.release();
+    c.sym_a.release(), c.sym_a_offs.release(), c.sym_b.release(), c.sym_b_offs.release(), c.scan_tmp.release(), c.flags.release(), c.hscratch.release();
 }
 
 extern "C" swb_status_t swb_scope_create(int first_device, int num_devices, swb_scope_t **out, const char **err) {
@@ -427,19 +428,27 @@ static swb_status_t launch_bitpar(swb_engine *eng, DeviceCtx &ctx, const PairSpa
     return SWB_OK;
 }
 
-// Returns SWB_TOO_LONG (without launching) when the staged strings do not fit in shared memory.
+// Lane-group bit-vector kernel: text streamed in shared-memory chunks, patterns beyond 32*G*K rows in row strips
+// through a global scratch row per pair — no length limit.
 template <int G, int K>
 static swb_status_t launch_bitpar_coop(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count,
                                        uint32_t max_m, uint32_t max_n, const char *name, cudaStream_t stream, const char **err) {
     constexpr int PPB = BPC_THREADS / G;
-    const uint32_t slot_rows = round16(max_m + 16u) + 16u, slot_cols = round16(max_n + 16u) + 16u;
-    const size_t smem = (size_t)32 * BPC_THREADS * K * 4 + (size_t)PPB * (slot_rows + slot_cols);
-    if (smem > (size_t)ctx.max_smem_optin) return fail(err, SWB_TOO_LONG, "strings of %u x %u bytes do not fit the bit-parallel kernel's shared memory", max_m, max_n);
+    constexpr uint32_t CAP = 32u * G * K;
+    const uint32_t chunk_cols = std::min<uint32_t>(1024u, std::max<uint32_t>(16u, round16(max_n)));
+    const size_t smem = (size_t)32 * BPC_THREADS * K * 4 + (size_t)PPB * (CAP + 32u + chunk_cols + 32u);
+    uint8_t *scratch = nullptr;
+    uint64_t scratch_stride = 0;
+    if (max_m > CAP) { // row strips: one byte of horizontal-delta bits per text column and pair
+        scratch_stride = round16(max_n) + 16u;
+        SWB_CUDA(ctx.hscratch.reserve(count * scratch_stride));
+        scratch = (uint8_t *)ctx.hscratch.ptr;
+    }
     SWB_CUDA(allow_smem((const void *)lev_bitpar_coop_kernel<G, K>, ctx.device, smem));
     const uint64_t blocks = (count + PPB - 1) / PPB;
     {
         ProfileBracket bracket(eng, ctx.device, stream);
-        lev_bitpar_coop_kernel<G, K><<<(unsigned)blocks, BPC_THREADS, smem, stream>>>(ps, begin, count, slot_rows, slot_cols);
+        lev_bitpar_coop_kernel<G, K><<<(unsigned)blocks, BPC_THREADS, smem, stream>>>(ps, begin, count, chunk_cols, scratch, scratch_stride);
     }
     g_launches++;
     eng->last_kernel = name;
@@ -544,13 +553,10 @@ static swb_status_t launch_class(swb_engine *eng, DeviceCtx &ctx, int dev_index,
         if (max_m <= 64) return launch_bitpar<2>(eng, ctx, ps, begin, count, stream, err);
         if (max_m <= 128) return launch_bitpar<4>(eng, ctx, ps, begin, count, stream, err);
         if (max_m <= 256) return launch_bitpar<8>(eng, ctx, ps, begin, count, stream, err);
-        swb_status_t st = SWB_TOO_LONG;
-        if (max_m <= 512) st = launch_bitpar_coop<8, 2>(eng, ctx, ps, begin, count, max_m, max_n, "lev_bitpar_coop<G=8,K=2>", stream, err);
-        else if (max_m <= 1024) st = launch_bitpar_coop<16, 2>(eng, ctx, ps, begin, count, max_m, max_n, "lev_bitpar_coop<G=16,K=2>", stream, err);
-        else if (max_m <= 2048) st = launch_bitpar_coop<32, 2>(eng, ctx, ps, begin, count, max_m, max_n, "lev_bitpar_coop<G=32,K=2>", stream, err);
-        else if (max_m <= 4096) st = launch_bitpar_coop<32, 4>(eng, ctx, ps, begin, count, max_m, max_n, "lev_bitpar_coop<G=32,K=4>", stream, err);
-        if (st != SWB_TOO_LONG) return st;
-        // beyond the lane-group kernels' capacity: the wavefront kernel's row strips (still exact)
+        if (max_m <= 512) return launch_bitpar_coop<8, 2>(eng, ctx, ps, begin, count, max_m, max_n, "lev_bitpar_coop<G=8,K=2>", stream, err);
+        if (max_m <= 1024) return launch_bitpar_coop<16, 2>(eng, ctx, ps, begin, count, max_m, max_n, "lev_bitpar_coop<G=16,K=2>", stream, err);
+        if (max_m <= 2048) return launch_bitpar_coop<32, 2>(eng, ctx, ps, begin, count, max_m, max_n, "lev_bitpar_coop<G=32,K=2>", stream, err);
+        return launch_bitpar_coop<32, 4>(eng, ctx, ps, begin, count, max_m, max_n, max_m <= 4096 ? "lev_bitpar_coop<G=32,K=4>" : "lev_bitpar_coop<G=32,K=4,strips>", stream, err);
     }
     return launch_wavefront(eng, ctx, dev_index, ps, begin, count, max_m, max_n, stream, err);
 }

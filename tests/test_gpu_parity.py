@@ -294,3 +294,30 @@ def test_load_phase_kernel_bytesums(scope, lev, gen):
     csb = np.concatenate([[0], np.cumsum(b.data.astype(np.int64))])
     want = (csa[a.offsets[1:].astype(np.int64)] - csa[a.offsets[:-1].astype(np.int64)]) + (csb[b.offsets[1:].astype(np.int64)] - csb[b.offsets[:-1].astype(np.int64)])
     assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_unbounded_lengths(scope, lev, oracle):
+    """Byte Levenshtein has no length limit: text streams through shared memory in chunks and patterns beyond
+    4096 bytes run in row strips (delta bits parked in global scratch between strips)."""
+    rng = np.random.default_rng(31)
+    alphabet = np.frombuffer(b"ACGT", dtype=np.uint8)
+    la = np.array([4097, 8192, 8193, 10_000, 20_000, 50, 3000, 12_289, 0, 9000])
+    lb = np.array([4097, 8192, 9000, 12_000, 20_001, 100_000, 70_000, 12_288, 5000, 9000])
+    a = datasets._ragged(la, alphabet, rng, False)
+    b = datasets._ragged(lb, alphabet, rng, False)
+    got = _check_pairs(lev, scope, oracle, a, b, sw.ALGO_AUTO)
+    assert got[8] == 5000
+    # near-identical long strings: small distance through many strips
+    base = bytes(rng.choice(alphabet, size=15_000))
+    near = bytearray(base)
+    for pos in rng.choice(15_000, size=25, replace=False):
+        near[pos] = ord("N")
+    a2, b2 = BytesTape.from_strings([base, base]), BytesTape.from_strings([bytes(near), base[7:]])
+    got = _check_pairs(lev, scope, oracle, a2, b2, sw.ALGO_AUTO)
+    assert list(got) == [25, 7]
+    # the wavefront family stages whole strings in shared memory and reports, not crashes, when they do not fit
+    lev.set_algorithm(sw.ALGO_WAVEFRONT)
+    with pytest.raises(sw.Error) as e:
+        lev.compute_pairs(scope, a, b)
+    assert e.value.status_name == "TOO_LONG"
+    lev.set_algorithm(sw.ALGO_AUTO)
