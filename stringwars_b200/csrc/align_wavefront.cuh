@@ -189,7 +189,11 @@ __global__ void __launch_bounds__(WF_THREADS)
                 if (AFFINE) s_be[j0 + 1] = (BoundT)max(up_e, e_floor);
             }
         };
+        // The shared-memory boundary row is updated in place: lane 0 reads column j long before lane G-1 parks the
+        // new value of column j. The per-step shuffle orders the two in execution; `__syncwarp()` makes that an
+        // explicit memory ordering too (shuffles are not memory barriers). Only on the paths that use the row.
         auto step_guarded = [&](const int(&Hold)[R], int(&Hnew)[R], uint32_t t) {
+            if (use_bound) __syncwarp();
             const int recv_h = __shfl_up_sync(0xffffffffu, Hold[R - 1], 1, G);
             int recv_e = e_floor;
             if (AFFINE) recv_e = __shfl_up_sync(0xffffffffu, send_e, 1, G);
@@ -197,6 +201,7 @@ __global__ void __launch_bounds__(WF_THREADS)
             if (j0 < n_live) cells(Hold, Hnew, j0, recv_h, recv_e);
         };
         auto step_steady = [&](const int(&Hold)[R], int(&Hnew)[R], uint32_t t) {
+            if (use_bound) __syncwarp();
             const int recv_h = __shfl_up_sync(0xffffffffu, Hold[R - 1], 1, G);
             int recv_e = e_floor;
             if (AFFINE) recv_e = __shfl_up_sync(0xffffffffu, send_e, 1, G);

@@ -444,11 +444,15 @@ static swb_status_t launch_bitpar_coop(swb_engine *eng, DeviceCtx &ctx, const Pa
         SWB_CUDA(ctx.hscratch.reserve(count * scratch_stride));
         scratch = (uint8_t *)ctx.hscratch.ptr;
     }
-    SWB_CUDA(allow_smem((const void *)lev_bitpar_coop_kernel<G, K>, ctx.device, smem));
     const uint64_t blocks = (count + PPB - 1) / PPB;
-    {
+    if (scratch) {
+        SWB_CUDA(allow_smem((const void *)lev_bitpar_coop_kernel<G, K, true>, ctx.device, smem));
         ProfileBracket bracket(eng, ctx.device, stream);
-        lev_bitpar_coop_kernel<G, K><<<(unsigned)blocks, BPC_THREADS, smem, stream>>>(ps, begin, count, chunk_cols, scratch, scratch_stride);
+        lev_bitpar_coop_kernel<G, K, true><<<(unsigned)blocks, BPC_THREADS, smem, stream>>>(ps, begin, count, chunk_cols, scratch, scratch_stride);
+    } else {
+        SWB_CUDA(allow_smem((const void *)lev_bitpar_coop_kernel<G, K, false>, ctx.device, smem));
+        ProfileBracket bracket(eng, ctx.device, stream);
+        lev_bitpar_coop_kernel<G, K, false><<<(unsigned)blocks, BPC_THREADS, smem, stream>>>(ps, begin, count, chunk_cols, scratch, scratch_stride);
     }
     g_launches++;
     eng->last_kernel = name;

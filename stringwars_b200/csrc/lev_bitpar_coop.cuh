@@ -24,7 +24,8 @@ namespace swb {
 
 constexpr int BPC_THREADS = 128;
 
-template <int G, int K>
+// STRIPS = false compiles the row-strip machinery out (every pattern of the launch fits CAP rows).
+template <int G, int K, bool STRIPS>
 __global__ void __launch_bounds__(BPC_THREADS)
     lev_bitpar_coop_kernel(PairSpace ps, uint64_t begin, uint64_t count, uint32_t chunk_cols, uint8_t *hscratch, uint64_t scratch_stride) {
     constexpr int T = BPC_THREADS, PAIRS_PER_BLOCK = T / G;
@@ -50,8 +51,8 @@ __global__ void __launch_bounds__(BPC_THREADS)
         pat = swap ? pv.b : pv.a, txt = swap ? pv.a : pv.b;
         out_index = pv.out_index;
     }
-    uint8_t *const hs = hscratch ? hscratch + local * scratch_stride : nullptr;
-    const uint32_t strips = (m + CAP - 1u) / CAP; // 0 for an empty pattern
+    uint8_t *const hs = (STRIPS && hscratch) ? hscratch + local * scratch_stride : nullptr;
+    const uint32_t strips = STRIPS ? (m + CAP - 1u) / CAP : (m ? 1u : 0u); // 0 for an empty pattern
     const uint32_t s = strips * CAP - m;          // pattern symbol i lives at global bit position s + i (s < CAP)
 
     uint32_t n_max = n, strips_max = strips;
@@ -96,9 +97,9 @@ __global__ void __launch_bounds__(BPC_THREADS)
             Pv[w] = s >= lo_bit + 32u ? 0u : (s <= lo_bit ? 0xFFFFFFFFu : 0xFFFFFFFFu << (s - lo_bit));
             Mv[w] = 0u;
         }
-        const bool from_scratch = r > 0 && lane == 0;            // delta bits come from the previous strip
-        const bool to_scratch = strip_live && r + 1 < strips && lane == G - 1; // ... or go to the next one
-        const bool scoring = strip_live && r + 1 == strips && lane == G - 1;
+        const bool from_scratch = STRIPS && r > 0 && lane == 0;                          // delta bits come from the previous strip
+        const bool to_scratch = STRIPS && strip_live && r + 1 < strips && lane == G - 1; // ... or go to the next one
+        if (r + 1 == strips) score = m; // only the last strip's last lane carries the distance (others: discarded)
         uint32_t send = 0;
 
         // ---- the text, one shared-memory chunk at a time
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(BPC_THREADS)
             const uint32_t mis_c = len_stage ? stage_string(cols_slot, txt + c0, len_stage, lane, G) : 0u;
             __syncwarp();
             const unsigned char *cols_s = cols_slot + mis_c;
-            uint32_t next_in = (from_scratch && len_c) ? hs[c0] : 0u; // prefetched delta bits of the next column
+            uint32_t next_in = (STRIPS && from_scratch && len_c) ? hs[c0] : 0u; // prefetched delta bits of the next column
             const uint32_t steps = min(n_max - c0, chunk_cols) + G - 1;
             for (uint32_t t = 0; t < steps; ++t) {
                 const uint32_t recv = __shfl_up_sync(0xffffffffu, send, 1, G);
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(BPC_THREADS)
                         }
                     }
                     uint32_t in = recv;
-                    if (from_scratch) {
+                    if (STRIPS && from_scratch) {
                         in = next_in;
                         if (jj + 1 < len_c) next_in = hs[c0 + jj + 1];
                     }
@@ -151,8 +152,8 @@ __global__ void __launch_bounds__(BPC_THREADS)
                         hp_in = ph >> 31, hn_in = mh >> 31;
                     }
                     send = hp_in | (hn_in << 1);
-                    if (scoring) score += hp_in - hn_in; // last pattern row = bit 31 of the last lane's last word
-                    if (to_scratch) hs[c0 + jj] = (uint8_t)send;
+                    score += hp_in - hn_in; // meaningful in the last lane only: last pattern row = bit 31 of its last word
+                    if (STRIPS && to_scratch) hs[c0 + jj] = (uint8_t)send;
                 }
             }
         }
