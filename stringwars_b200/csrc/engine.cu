@@ -23,6 +23,7 @@
 #include "align_wavefront.cuh"
 #include "lev_bitpar.cuh"
 #include "lev_bitpar_coop.cuh"
+#include "lev_bitpar_cross.cuh"
 #include "schedule.cuh"
 #include "utf8.cuh"
 
@@ -546,6 +547,25 @@ static swb_status_t launch_wavefront(swb_engine *eng, DeviceCtx &ctx, int dev_in
     return st;
 }
 
+// Cross product with table reuse: one thread per query, candidates swept (lev_bitpar_cross.cuh).
+template <int K>
+static swb_status_t launch_bitpar_cross(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint32_t n_queries, uint32_t cands_per_block,
+                                        const char *name, cudaStream_t stream, const char **err) {
+    constexpr int T = BitparConfig<K>::THREADS;
+    const uint32_t chunk = 1024;
+    const size_t smem = (size_t)32 * T * K * 4 + chunk + 32;
+    SWB_CUDA(allow_smem((const void *)lev_bitpar_cross_kernel<K>, ctx.device, smem));
+    const dim3 grid((n_queries + T - 1) / T, (unsigned)((ps.n_c + cands_per_block - 1) / cands_per_block));
+    {
+        ProfileBracket bracket(eng, ctx.device, stream);
+        lev_bitpar_cross_kernel<K><<<grid, T, smem, stream>>>(ps, n_queries, cands_per_block, chunk);
+    }
+    g_launches++;
+    eng->last_kernel = name;
+    SWB_CUDA(cudaGetLastError());
+    return SWB_OK;
+}
+
 // One length class of one batch on one device.
 static swb_status_t launch_class(swb_engine *eng, DeviceCtx &ctx, int dev_index, const PairSpace &ps, uint64_t begin,
                                  uint64_t count, uint32_t max_m, uint32_t max_n, cudaStream_t stream, const char **err) {
@@ -643,6 +663,30 @@ static swb_status_t run_device_batch(swb_engine *eng, int dev_index, PairSpace p
     if (ps.n_pairs == 0) return SWB_OK;
     if (ps.n_pairs >= 0xFFFFFFFFull) return fail(err, SWB_INVALID_ARG, "more than 2^32-1 pairs in one call");
     ps.order = nullptr;
+    // Cross products large enough to amortise a per-query table build: statistics of the QUERY tape alone decide
+    // the kernel (queries are the patterns), then one thread per query sweeps its share of the candidates.
+    if (ps.n_c >= 32 && ps.len_shift == 0 && (eng->kind == ENGINE_LEVENSHTEIN || eng->kind == ENGINE_LEVENSHTEIN_UTF8) &&
+        eng->algorithm != SWB_ALGO_WAVEFRONT) {
+        const uint64_t n_q = ps.n_pairs / ps.n_c;
+        PairSpace qs = ps; // degenerate pair space (q_i, q_i): its counters are the query-length statistics
+        qs.b_data = ps.a_data, qs.b_offs = ps.a_offs, qs.n_pairs = n_q, qs.n_c = 0;
+        swb_status_t qst = enqueue_schedule_count(ctx, qs, stream, err);
+        if (qst != SWB_OK) return qst;
+        if ((qst = wait_schedule_count(ctx, err)) != SWB_OK) return qst;
+        uint32_t max_q = 0;
+        for (int c = 0; c < SCHED_MCLASSES; ++c) max_q = std::max(max_q, ctx.h_stats->max_m[c]);
+        // candidates per block: enough blocks to fill the machine twice, at least 16 candidates per table build
+        const uint64_t query_blocks = (n_q + 127) / 128;
+        uint64_t cpb = std::max<uint64_t>(16, ps.n_c * query_blocks / std::max<uint64_t>(1, (uint64_t)ctx.sm_count * 8));
+        cpb = std::min<uint64_t>(cpb, ps.n_c);
+        const bool worth = max_q <= 256 && query_blocks * ((ps.n_c + cpb - 1) / cpb) >= (uint64_t)ctx.sm_count;
+        if (worth) {
+            if (max_q <= 32) return launch_bitpar_cross<1>(eng, ctx, ps, (uint32_t)n_q, (uint32_t)cpb, "lev_bitpar_cross<K=1>", stream, err);
+            if (max_q <= 64) return launch_bitpar_cross<2>(eng, ctx, ps, (uint32_t)n_q, (uint32_t)cpb, "lev_bitpar_cross<K=2>", stream, err);
+            if (max_q <= 128) return launch_bitpar_cross<4>(eng, ctx, ps, (uint32_t)n_q, (uint32_t)cpb, "lev_bitpar_cross<K=4>", stream, err);
+            return launch_bitpar_cross<8>(eng, ctx, ps, (uint32_t)n_q, (uint32_t)cpb, "lev_bitpar_cross<K=8>", stream, err);
+        }
+    }
     // Speculate that this batch has the shape of the previous one. A thread-per-pair bit-vector kernel is correct
     // for every pair that fits its K words and skips the others, and its launch geometry depends on nothing but
     // the pair count, so it goes onto the caller's stream IMMEDIATELY while the schedule kernel runs beside it on

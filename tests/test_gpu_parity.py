@@ -321,3 +321,28 @@ def test_unbounded_lengths(scope, lev, oracle):
         lev.compute_pairs(scope, a, b)
     assert e.value.status_name == "TOO_LONG"
     lev.set_algorithm(sw.ALGO_AUTO)
+
+
+def test_cross_product_table_reuse_kernel(scope, lev, oracle):
+    """Cross products large enough to amortise a per-query table build take `lev_bitpar_cross` (one thread per
+    query, candidates swept out of shared memory). Covers every K, empty strings, candidates beyond one chunk."""
+    rng = np.random.default_rng(41)
+    alphabet = np.frombuffer(b"ACGT", dtype=np.uint8)
+    words = datasets.words_pairs(1400, seed=3)[0]
+    cases = [
+        (words.subview(0, 600), words.subview(600, 1300)),                                             # K=1, ragged
+        (datasets.ascii_pairs(700, 64, seed=2)[0], datasets.ascii_pairs(450, 64, seed=3)[1]),         # K=2
+        (datasets._ragged(rng.integers(0, 129, 700), alphabet, rng, False), datasets._ragged(rng.integers(0, 300, 500), alphabet, rng, False)),  # K=4, empties
+        (datasets._ragged(rng.integers(100, 257, 900), alphabet, rng, False), datasets._ragged(rng.integers(900, 2600, 300), alphabet, rng, False)),  # K=8, multi-chunk
+    ]
+    for q, c in cases:
+        got = lev.compute(scope, q, c)
+        assert "cross" in lev.last_kernel, lev.last_kernel
+        want = oracle.levenshtein_cross(q.data, q.offsets, c.data, c.offsets, oracle.RAPIDFUZZ_CLASS, threads=16)
+        bad = np.argwhere(got != want)
+        assert bad.size == 0, (bad[:5], lev.last_kernel)
+    # row stride wider than the candidate count, untouched padding
+    q, c = cases[0]
+    wide = np.full((len(q), len(c) + 5), 777, dtype=np.uint64)
+    lev.compute_into(scope, q, c, wide)
+    assert (wide[:, len(c):] == 777).all() and np.array_equal(wide[:, :len(c)], oracle.levenshtein_cross(q.data, q.offsets, c.data, c.offsets, threads=16))
