@@ -572,6 +572,11 @@ static swb_status_t launch_class(swb_engine *eng, DeviceCtx &ctx, int dev_index,
     if (count == 0) return SWB_OK;
     const bool lev_bytes = (eng->kind == ENGINE_LEVENSHTEIN || eng->kind == ENGINE_LEVENSHTEIN_UTF8) && ps.len_shift == 0;
     if (lev_bytes && eng->algorithm != SWB_ALGO_WAVEFRONT) {
+        // SWB_EXP (bit mask, experiments only): 1: <=256 B via lane groups <4,2>; 2: <=1024 B via <8,4>; 4: <=512 B via <4,4>
+        static const int exp_mask = getenv("SWB_EXP") ? atoi(getenv("SWB_EXP")) : 0;
+        if ((exp_mask & 1) && max_m > 128 && max_m <= 256) return launch_bitpar_coop<4, 2>(eng, ctx, ps, begin, count, max_m, max_n, "lev_bitpar_coop<G=4,K=2>", stream, err);
+        if ((exp_mask & 4) && max_m > 256 && max_m <= 512) return launch_bitpar_coop<4, 4>(eng, ctx, ps, begin, count, max_m, max_n, "lev_bitpar_coop<G=4,K=4>", stream, err);
+        if ((exp_mask & 2) && max_m > 512 && max_m <= 1024) return launch_bitpar_coop<8, 4>(eng, ctx, ps, begin, count, max_m, max_n, "lev_bitpar_coop<G=8,K=4>", stream, err);
         // thread-per-pair bit-vector kernels up to 256 pattern bytes, lane-group kernels up to 4096
         if (max_m <= 32) return launch_bitpar<1>(eng, ctx, ps, begin, count, stream, err);
         if (max_m <= 64) return launch_bitpar<2>(eng, ctx, ps, begin, count, stream, err);

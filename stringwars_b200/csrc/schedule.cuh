@@ -144,7 +144,7 @@ constexpr int LOAD_THREADS = 256;
 constexpr int LOAD_PAIRS = 256;
 
 __device__ __forceinline__ uint32_t masked_sum16(const uint8_t *piece, int lo, int hi) {
-    // sum of bytes [lo, hi) of the 16-byte shared-memory piece
+    // sum of bytes [lo, hi) of the 16-byte shared-memory piece (ragged head / tail of a string)
     const uint4 v = *reinterpret_cast<const uint4 *>(piece);
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     uint32_t acc = 0;
@@ -157,6 +157,31 @@ __device__ __forceinline__ uint32_t masked_sum16(const uint8_t *piece, int lo, i
         if (b1 < 4) x &= 0xFFFFFFFFu >> (8 * (4 - b1));
         acc = __dp4a(x, 0x01010101u, acc);
     }
+    return acc;
+}
+
+__device__ __forceinline__ uint32_t whole_sum16(const uint8_t *piece) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(piece);
+    uint32_t acc = __dp4a(v.x, 0x01010101u, 0u);
+    acc = __dp4a(v.y, 0x01010101u, acc);
+    acc = __dp4a(v.z, 0x01010101u, acc);
+    return __dp4a(v.w, 0x01010101u, acc);
+}
+
+// Byte sum of the string occupying bytes [s, e) of a staged span: only a ragged head or tail piece pays for
+// masks, every whole piece is one LDS.128 + four DP4A (the first version masked every piece and made this
+// measurement kernel instruction-bound: issue 81 %, profiles/r1_c_load_phase_ascii64.txt).
+__device__ __forceinline__ uint32_t span_sum(const uint8_t *span, uint32_t s, uint32_t e) {
+    if (e <= s) return 0u;
+    uint32_t acc = 0;
+    uint32_t q = s >> 4;
+    const uint32_t q_end = e >> 4; // pieces [q, q_end) lie wholly inside once the head is handled
+    if (s & 15u) {
+        acc = masked_sum16(span + 16u * q, (int)(s & 15u), (int)min(16u, e - 16u * q));
+        ++q;
+    }
+    for (; q < q_end; ++q) acc += whole_sum16(span + 16u * q);
+    if ((e & 15u) && q == q_end) acc += masked_sum16(span + 16u * q, 0, (int)(e & 15u));
     return acc;
 }
 
@@ -223,16 +248,8 @@ __global__ void __launch_bounds__(LOAD_THREADS) load_phase_kernel(PairSpace ps, 
             const LoadTileMeta mt = meta[stage];
             const uint8_t *s_a = lsm + (size_t)stage * stage_bytes, *s_b = s_a + cap_a;
             uint32_t acc = 0;
-            {
-                const uint32_t s = mt.mis_a + (uint32_t)(oa0 - mt.a_lo), e = mt.mis_a + (uint32_t)(oa1 - mt.a_lo);
-                for (uint32_t q = s >> 4; q < (e + 15u) >> 4; ++q)
-                    acc += masked_sum16(s_a + 16u * q, (int)max(s, 16u * q) - (int)(16u * q), (int)min(e, 16u * q + 16u) - (int)(16u * q));
-            }
-            {
-                const uint32_t s = mt.mis_b + (uint32_t)(ob0 - mt.b_lo), e = mt.mis_b + (uint32_t)(ob1 - mt.b_lo);
-                for (uint32_t q = s >> 4; q < (e + 15u) >> 4; ++q)
-                    acc += masked_sum16(s_b + 16u * q, (int)max(s, 16u * q) - (int)(16u * q), (int)min(e, 16u * q + 16u) - (int)(16u * q));
-            }
+            acc += span_sum(s_a, mt.mis_a + (uint32_t)(oa0 - mt.a_lo), mt.mis_a + (uint32_t)(oa1 - mt.a_lo));
+            acc += span_sum(s_b, mt.mis_b + (uint32_t)(ob0 - mt.b_lo), mt.mis_b + (uint32_t)(ob1 - mt.b_lo));
             ps.out[p] = acc;
         }
         __syncthreads(); // stage `stage` may be refilled (and its meta rewritten) from the next iteration on
@@ -270,16 +287,8 @@ __global__ void __launch_bounds__(LOAD_THREADS) load_phase_simple_kernel(PairSpa
     }
     if (p < p1) {
         uint32_t acc = 0;
-        {
-            const uint32_t s = mis_a + (uint32_t)(oa0 - a_lo), e = mis_a + (uint32_t)(oa1 - a_lo);
-            for (uint32_t q = s >> 4; q < (e + 15u) >> 4; ++q)
-                acc += masked_sum16(s_a + 16u * q, (int)max(s, 16u * q) - (int)(16u * q), (int)min(e, 16u * q + 16u) - (int)(16u * q));
-        }
-        {
-            const uint32_t s = mis_b + (uint32_t)(ob0 - b_lo), e = mis_b + (uint32_t)(ob1 - b_lo);
-            for (uint32_t q = s >> 4; q < (e + 15u) >> 4; ++q)
-                acc += masked_sum16(s_b + 16u * q, (int)max(s, 16u * q) - (int)(16u * q), (int)min(e, 16u * q + 16u) - (int)(16u * q));
-        }
+        acc += span_sum(s_a, mis_a + (uint32_t)(oa0 - a_lo), mis_a + (uint32_t)(oa1 - a_lo));
+        acc += span_sum(s_b, mis_b + (uint32_t)(ob0 - b_lo), mis_b + (uint32_t)(ob1 - b_lo));
         ps.out[p] = acc;
     }
 }
