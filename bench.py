@@ -318,6 +318,13 @@ def main():
                           "checksum": sg_checksum}
 
     peak, peak_src = measured_peaks()
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes per launch of this kernel on this workload, from the committed ncu --set full capture
+        entry = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{kernel_name}|{args.workload}|{n_pairs}")
+        if entry:
+            traffic, traffic_src = entry["traffic"], entry["source"]
+    except Exception:
+        pass
     achieved = bytes_step_alg / (kernel_ms / max(kernel_launches, 1) * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
     load_gbs = bytes_step_alg / (load_ms / max(load_n, 1) * 1e-3) / 1e9 if load_ms > 0 else 0.0
 
@@ -338,7 +345,7 @@ def main():
                     "h2d_bytes_per_step": int(bytes_step_alg + 2 * 8 * (n_pairs + 1)), "d2h_bytes_per_step": 8 * n_pairs,
                     "api": "swb_compute_pairs (host tapes, pinned)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": kernel_name, "kernel_ms": kernel_ms / max(kernel_launches, 1), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_step_alg,
                          "kernel_gcups": cells_step / (kernel_ms / max(kernel_launches, 1) * 1e-3) / 1e9 if kernel_ms else None,
