@@ -60,7 +60,7 @@ typedef enum swb_gap_convention_t {
 } swb_gap_convention_t;
 
 typedef struct swb_scope swb_scope_t;   /* replaces `szs::DeviceScope`            (bench.rs:376-379) */
-typedef struct swb_engine swb_engine_t; /* replaces the `szs::*Distances/*Scores` engines (bench.rs:382-399, 658-674) */
+typedef struct swb_engine swb_engine_t; /* replaces the `szs` Distances / Scores engines (bench.rs:382-399, 658-674) */
 
 /* ---- library / device queries ------------------------------------------------------------------------- */
 

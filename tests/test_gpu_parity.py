@@ -346,3 +346,22 @@ def test_cross_product_table_reuse_kernel(scope, lev, oracle):
     wide = np.full((len(q), len(c) + 5), 777, dtype=np.uint64)
     lev.compute_into(scope, q, c, wide)
     assert (wide[:, len(c):] == 777).all() and np.array_equal(wide[:, :len(c)], oracle.levenshtein_cross(q.data, q.offsets, c.data, c.offsets, threads=16))
+
+
+def test_cpp_harness_twin_runs(tmp_path):
+    """The compiled C++ twin of the reference harness's GPU blocks builds against the C ABI and runs every
+    variant once (STRINGWARS_TIME=0 is the reference's own smoke mode, bench.rs:34-40)."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "harness"), "-B"], check=True, capture_output=True)
+    env = dict(os.environ, STRINGWARS_TIME="0", STRINGWARS_WARMUP="0", STRINGWARS_MAX_TOKENS="20000")
+    out = subprocess.run([os.path.join(root, "harness", "bench_similarities")], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    for variant in ("uniform/stringwars_b200::levenshtein<1gpu>", "uniform/stringwars_b200::levenshtein_utf8<1gpu>",
+                    "linear/stringwars_b200::needleman_wunsch<1gpu>", "affine/stringwars_b200::smith_waterman<1gpu>"):
+        assert variant in out.stdout, out.stdout
+    assert "CUPS" in out.stdout and "checksum=" in out.stderr
+    # the regex filter of the reference (utils.rs:457-483) applies to our variant names too
+    env["STRINGWARS_FILTER"] = "needleman"
+    out = subprocess.run([os.path.join(root, "harness", "bench_similarities")], env=env, capture_output=True, text=True, timeout=300)
+    assert "needleman_wunsch" in out.stdout and "levenshtein<1gpu>" not in out.stdout
