@@ -21,6 +21,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "align_wavefront.cuh"
+#include "align_wavefront_packed.cuh"
 #include "lev_bitpar.cuh"
 #include "lev_bitpar_coop.cuh"
 #include "lev_bitpar_cross.cuh"
@@ -487,6 +488,27 @@ static swb_status_t launch_wavefront_t(swb_engine *eng, DeviceCtx &ctx, int dev_
     return SWB_OK;
 }
 
+// Two pairs per lane group in packed s16x2 registers (align_wavefront_packed.cuh). SWB_TOO_LONG = does not fit smem.
+template <int G, int R>
+static swb_status_t launch_wavefront_packed(swb_engine *eng, DeviceCtx &ctx, int dev_index, const PairSpace &ps, uint64_t begin, uint64_t count,
+                                            const AlignCosts &cs, uint32_t max_m, uint32_t max_n, cudaStream_t stream, const char **err) {
+    constexpr int GPB = WF_THREADS / G;
+    const bool single_strip = max_m <= (uint32_t)(G * R);
+    const uint32_t slot_rows = round16(max_m + 16u) + 16u, slot_cols = round16(max_n + 16u) + 16u;
+    const uint32_t bound_cap = single_strip ? 0u : max_n + 1u;
+    const size_t smem = 2304 + (size_t)GPB * (2u * slot_rows + 2u * slot_cols + round16(bound_cap * 4u));
+    if (smem > (size_t)ctx.max_smem_optin) return fail(err, SWB_TOO_LONG, "packed wavefront: %zu B of shared memory per block", smem);
+    SWB_CUDA(allow_smem((const void *)align_wavefront_packed_kernel<G, R>, ctx.device, smem));
+    const uint64_t blocks = ((count + 1) / 2 + GPB - 1) / GPB;
+    {
+        ProfileBracket bracket(eng, ctx.device, stream);
+        align_wavefront_packed_kernel<G, R><<<(unsigned)blocks, WF_THREADS, smem, stream>>>(ps, begin, count, cs, eng->d_tables[dev_index], slot_rows, slot_cols, bound_cap);
+    }
+    g_launches++;
+    SWB_CUDA(cudaGetLastError());
+    return SWB_OK;
+}
+
 template <int G, int R>
 static swb_status_t launch_wavefront_gr(swb_engine *eng, DeviceCtx &ctx, int dev_index, const PairSpace &ps, uint64_t begin,
                                         uint64_t count, const AlignCosts &cs, bool local, bool affine, bool unary, bool narrow,
@@ -514,7 +536,7 @@ static swb_status_t launch_wavefront_gr(swb_engine *eng, DeviceCtx &ctx, int dev
 }
 
 static swb_status_t launch_wavefront(swb_engine *eng, DeviceCtx &ctx, int dev_index, const PairSpace &ps, uint64_t begin,
-                                     uint64_t count, uint32_t max_m, uint32_t max_n, cudaStream_t stream, const char **err) {
+                                     uint64_t count, uint32_t max_m, uint32_t max_n, cudaStream_t stream, const char **err, bool same_shape = false) {
     AlignCosts cs;
     const bool is_lev = eng->kind == ENGINE_LEVENSHTEIN || eng->kind == ENGINE_LEVENSHTEIN_UTF8;
     cs.match = eng->match, cs.mismatch = eng->mismatch;
@@ -529,6 +551,27 @@ static swb_status_t launch_wavefront(swb_engine *eng, DeviceCtx &ctx, int dev_in
     if (eng->unary) maxabs = std::max(maxabs, std::max(std::abs(cs.match), std::abs(cs.mismatch)));
     else maxabs = std::max(maxabs, 128);
     const bool narrow = (uint64_t)(max_m + max_n + 2u) * 3u * (uint64_t)maxabs < 30000u;
+    // Packed s16x2 variant (two pairs per lane group, half the ALU instructions per cell): global, linear gaps,
+    // unary costs, byte symbols, every pair of the same shape, shifted costs and scores inside 15 bits.
+    static const bool packed_off = getenv("SWB_NO_PACKED") != nullptr;
+    const int cm_s = cs.match - 2 * cs.next, cx_s = cs.mismatch - 2 * cs.next;
+    if (!packed_off && same_shape && !local && !affine && eng->unary && ps.len_shift == 0 && count >= 2 && cx_s >= 0 && cm_s >= cx_s &&
+        (uint64_t)(std::min(max_m, max_n) + 1u) * (uint64_t)cm_s < 32000u) {
+        swb_status_t pst = SWB_TOO_LONG;
+#define SWB_PK(G, NAME)                                                                                                   \
+        if (pst == SWB_TOO_LONG && (max_m <= (uint32_t)(G) * 16u || (G) == 32)) {                                           \
+            eng->last_kernel = NAME;                                                                                      \
+            pst = launch_wavefront_packed<G, 16>(eng, ctx, dev_index, ps, begin, count, cs, max_m, max_n, stream, err);   \
+        }
+        SWB_PK(1, "align_wavefront_packed<G=1,R=16>")
+        SWB_PK(2, "align_wavefront_packed<G=2,R=16>")
+        SWB_PK(4, "align_wavefront_packed<G=4,R=16>")
+        SWB_PK(8, "align_wavefront_packed<G=8,R=16>")
+        SWB_PK(16, "align_wavefront_packed<G=16,R=16>")
+        SWB_PK(32, "align_wavefront_packed<G=32,R=16>")
+#undef SWB_PK
+        if (pst != SWB_TOO_LONG) return pst;
+    }
     // Narrowest group that covers the pattern in one strip; if the class's longest text makes the block's staged
     // strings overflow shared memory (lopsided pairs), widen the group: fewer pairs per block, same kernel.
     swb_status_t st = SWB_TOO_LONG;
@@ -568,7 +611,7 @@ static swb_status_t launch_bitpar_cross(swb_engine *eng, DeviceCtx &ctx, const P
 
 // One length class of one batch on one device.
 static swb_status_t launch_class(swb_engine *eng, DeviceCtx &ctx, int dev_index, const PairSpace &ps, uint64_t begin,
-                                 uint64_t count, uint32_t max_m, uint32_t max_n, cudaStream_t stream, const char **err) {
+                                 uint64_t count, uint32_t max_m, uint32_t max_n, cudaStream_t stream, const char **err, bool same_shape = false) {
     if (count == 0) return SWB_OK;
     const bool lev_bytes = (eng->kind == ENGINE_LEVENSHTEIN || eng->kind == ENGINE_LEVENSHTEIN_UTF8) && ps.len_shift == 0;
     if (lev_bytes && eng->algorithm != SWB_ALGO_WAVEFRONT) {
@@ -587,7 +630,7 @@ static swb_status_t launch_class(swb_engine *eng, DeviceCtx &ctx, int dev_index,
         if (max_m <= 2048) return launch_bitpar_coop<32, 2>(eng, ctx, ps, begin, count, max_m, max_n, "lev_bitpar_coop<G=32,K=2>", stream, err);
         return launch_bitpar_coop<32, 4>(eng, ctx, ps, begin, count, max_m, max_n, max_m <= 4096 ? "lev_bitpar_coop<G=32,K=4>" : "lev_bitpar_coop<G=32,K=4,strips>", stream, err);
     }
-    return launch_wavefront(eng, ctx, dev_index, ps, begin, count, max_m, max_n, stream, err);
+    return launch_wavefront(eng, ctx, dev_index, ps, begin, count, max_m, max_n, stream, err, same_shape);
 }
 
 // Schedule counters for a device-resident PairSpace: enqueue the count kernel on `stream`; it publishes into
@@ -628,6 +671,7 @@ static swb_status_t wait_schedule_count(DeviceCtx &ctx, const char **err) {
 
 struct Plan {
     bool identity = true;        // single key: keep input order
+    bool same_shape = false;     // every pair has the same (shorter, longer) lengths
     int n_classes = 0;
     int cls[SCHED_MCLASSES];     // pattern-length class index of each entry
     uint64_t begin[SCHED_MCLASSES], count[SCHED_MCLASSES];
@@ -658,6 +702,7 @@ static Plan make_plan(ScheduleStats &st) {
     }
     // one pattern class and at most two text-length bins: the indirection would cost more than the divergence
     plan.identity = plan.n_classes <= 1 && nonempty_keys <= 2;
+    plan.same_shape = plan.n_classes == 1 && st.min_m == plan.max_m[0] && st.min_n == plan.max_n[0];
     return plan;
 }
 
@@ -727,7 +772,7 @@ static swb_status_t run_device_batch(swb_engine *eng, int dev_index, PairSpace p
         ps.order = (const uint32_t *)ctx.order.ptr;
     }
     for (int i = 0; i < plan.n_classes; ++i) {
-        st = launch_class(eng, ctx, dev_index, ps, plan.begin[i], plan.count[i], plan.max_m[i], plan.max_n[i], stream, err);
+        st = launch_class(eng, ctx, dev_index, ps, plan.begin[i], plan.count[i], plan.max_m[i], plan.max_n[i], stream, err, plan.same_shape);
         if (st != SWB_OK) return st;
     }
     return SWB_OK;
@@ -1015,7 +1060,7 @@ extern "C" swb_status_t swb_compute_pairs(swb_engine_t *engine, const uint8_t *a
             for (int c = 0; c < chunks; ++c) {
                 const uint64_t p0 = sh.chunk_cut[c] - sh.lo, p1 = sh.chunk_cut[c + 1] - sh.lo;
                 SWB_CUDA(cudaStreamWaitEvent(ctx.compute_stream, ctx.ev_chunks[c], 0));
-                if ((st = launch_class(engine, ctx, d, sh.ps, p0, p1 - p0, plan.max_m[0], plan.max_n[0], ctx.compute_stream, err)) != SWB_OK) return st;
+                if ((st = launch_class(engine, ctx, d, sh.ps, p0, p1 - p0, plan.max_m[0], plan.max_n[0], ctx.compute_stream, err, plan.same_shape)) != SWB_OK) return st;
                 SWB_CUDA(cudaMemcpyAsync(out + sh.lo + p0, (uint64_t *)ctx.out.ptr + p0, (p1 - p0) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx.compute_stream));
             }
         } else {
