@@ -15,9 +15,9 @@
 //
 // Instruction-level design (the kernel is ALU-pipe bound, ncu: profiles/r1_*):
 //  * The pattern is TOP-aligned: symbol i sits at bit s+i, s = 32K-m. The s rows below it are "free" rows
-//    (vertical delta 0, never matching) that replicate DP row 0, so the result is unchanged while the last
-//    pattern row is always bit 31 of word K-1: the score update is two shifts, no runtime bit index, no
-//    per-word predication.
+//    (vertical delta 0, never matching) that replicate DP row 0, so the result is unchanged and no bit index
+//    depends on m at run time.
+//  * The distance is not tracked per column at all: D[m][n] = n + popc(Pv) - popc(Mv) of the final column.
 //  * `x << 1 | carry` is written as x*2+carry and the adds as mul-adds: they issue on the FMA pipe (IMAD),
 //    which is otherwise idle, instead of the saturated ALU pipe.
 //  * Symbols are nibble-split four at a time ((w >> 4) & 0x0F0F0F0F, w & 0x0F0F0F0F); a table address is one
@@ -151,8 +151,8 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
         Pv[w] = s >= lo_bit + 32u ? 0u : (s <= lo_bit ? 0xFFFFFFFFu : 0xFFFFFFFFu << (s - lo_bit));
         Mv[w] = 0u;
     }
-    uint32_t score = m;
-
+    // No score is tracked per column: D[m][n] = D[0][n] + (sum of the vertical deltas of column n)
+    //                                          = n + popc(Pv) - popc(Mv) at the end (free rows carry delta 0).
     auto step = [&](uint32_t h, uint32_t l) {
         uint32_t hi[K], lo[K];
         load_words<K, T>(tbl_hi + h * ESTRIDE, tid, hi);
@@ -169,10 +169,8 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
             const uint32_t mhs = mh * 2u + hn_in;
             Pv[w] = mhs | ~(xv | phs);
             Mv[w] = phs & xv;
-            hp_in = ph >> 31, hn_in = mh >> 31;
+            if (w + 1 < K) hp_in = ph >> 31, hn_in = mh >> 31; // carries into the next word; none leave the last one
         }
-        score += hp_in; // the last pattern row is bit 31 of word K-1
-        score -= hn_in;
     };
     auto step4 = [&](uint32_t word) {
         const uint32_t wh = (word >> 4) & 0x0F0F0F0Fu, wl = word & 0x0F0F0F0Fu;
@@ -205,6 +203,9 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
             step(c >> 4, c & 15u);
         }
     }
+    uint32_t score = n;
+#pragma unroll
+    for (int w = 0; w < K; ++w) score += __popc(Pv[w]) - __popc(Mv[w]);
     ps.out[pv.out_index] = score;
 }
 

@@ -12,9 +12,9 @@
 //    carries over; each chunk costs G-1 fill/drain steps);
 //  * a PATTERN longer than CAP is processed in row strips of CAP rows; the two delta bits leaving a strip's last
 //    lane are parked per column in a global scratch row (1 byte per column) and fed to lane 0 of the next strip.
-// The pattern is top-aligned over all strips (see lev_bitpar.cuh), so the distance accumulates only in the last
-// lane of the last strip, and lanes of strip 0 that hold nothing but free rows stay idle (the first lane holding
-// pattern rows takes the constant +1 delta of DP row 0).
+// The pattern is top-aligned over all strips (see lev_bitpar.cuh); lanes of strip 0 that hold nothing but free rows
+// stay idle (the first lane holding pattern rows takes the constant +1 delta of DP row 0). The distance is
+// n + sum of popc(Pv) - popc(Mv) over all lanes and strips after the last column: nothing is tracked per step.
 //
 // <G,K> = <8,2> 512, <16,2> 1024, <32,2> 2048, <32,4> 4096 rows per strip. Parity: bit-exact with the CPU oracle.
 #pragma once
@@ -61,7 +61,9 @@ __global__ void __launch_bounds__(BPC_THREADS)
         n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, d));
         strips_max = max(strips_max, __shfl_xor_sync(0xffffffffu, strips_max, d));
     }
-    uint32_t score = m;
+    // D[m][n] = n + (sum of the vertical deltas of the last column) = n + sum over strips and lanes of
+    // popc(Pv) - popc(Mv) after the last column; nothing is tracked per step.
+    int delta_sum = 0;
 
     for (uint32_t r = 0; r < strips_max; ++r) {
         const bool strip_live = have && r < strips;
@@ -99,7 +101,6 @@ __global__ void __launch_bounds__(BPC_THREADS)
         }
         const bool from_scratch = STRIPS && r > 0 && lane == 0;                          // delta bits come from the previous strip
         const bool to_scratch = STRIPS && strip_live && r + 1 < strips && lane == G - 1; // ... or go to the next one
-        if (r + 1 == strips) score = m; // only the last strip's last lane carries the distance (others: discarded)
         uint32_t send = 0;
 
         // ---- the text, one shared-memory chunk at a time
@@ -152,13 +153,18 @@ __global__ void __launch_bounds__(BPC_THREADS)
                         hp_in = ph >> 31, hn_in = mh >> 31;
                     }
                     send = hp_in | (hn_in << 1);
-                    score += hp_in - hn_in; // meaningful in the last lane only: last pattern row = bit 31 of its last word
                     if (STRIPS && to_scratch) hs[c0 + jj] = (uint8_t)send;
                 }
             }
         }
+        if (lane_live) { // this lane's rows of this strip have seen the whole text
+#pragma unroll
+            for (int w = 0; w < K; ++w) delta_sum += __popc(Pv[w]) - __popc(Mv[w]);
+        }
     }
-    if (have && lane == G - 1) ps.out[out_index] = m == 0 ? n : score;
+#pragma unroll
+    for (int d = G / 2; d >= 1; d >>= 1) delta_sum += __shfl_xor_sync(0xffffffffu, delta_sum, d, G);
+    if (have && lane == G - 1) ps.out[out_index] = (uint64_t)((int64_t)n + delta_sum);
 }
 
 } // namespace swb

@@ -65,7 +65,6 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS)
         uint32_t Pv[K], Mv[K];
 #pragma unroll
         for (int w = 0; w < K; ++w) Pv[w] = Pv0[w], Mv[w] = 0u;
-        uint32_t score = m;
         auto step = [&](uint32_t h, uint32_t l) {
             uint32_t hi[K], lo[K];
             load_words<K, T>(tbl_hi + h * ESTRIDE, tid, hi);
@@ -82,10 +81,8 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS)
                 const uint32_t mhs = mh * 2u + hn_in;
                 Pv[w] = mhs | ~(xv | phs);
                 Mv[w] = phs & xv;
-                hp_in = ph >> 31, hn_in = mh >> 31;
+                if (w + 1 < K) hp_in = ph >> 31, hn_in = mh >> 31;
             }
-            score += hp_in;
-            score -= hn_in;
         };
         for (uint32_t c0 = 0; c0 < n; c0 += chunk) {
             const uint32_t len = min(n - c0, chunk);
@@ -114,6 +111,9 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS)
                 }
             }
         }
+        uint32_t score = n; // D[m][n] = n + popc(Pv) - popc(Mv) of the final column (free rows carry delta 0)
+#pragma unroll
+        for (int w = 0; w < K; ++w) score += __popc(Pv[w]) - __popc(Mv[w]);
         if (have && fits) ps.out[(uint64_t)q * ps.stride + c] = m == 0 ? n : score;
     }
 }
