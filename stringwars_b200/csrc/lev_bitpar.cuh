@@ -61,6 +61,52 @@ __device__ __forceinline__ void load_words(const unsigned char *entry, int tid, 
     }
 }
 
+// Table build for TWO aligned 16-symbol pieces that live in DIFFERENT table words (and, per piece, the HI and the
+// LO table): four read-modify-write chains through shared memory that can never touch the same address, so each
+// symbol step loads all four words first and stores them afterwards (the compiler cannot prove the independence
+// itself and otherwise serialises LDS -> OR -> STS four times; a single chain was 49 % of this kernel's stall
+// samples, profiles/r1_d_*).
+template <uint32_t ESTRIDE>
+__device__ __forceinline__ void build_piece_pair(unsigned char *__restrict__ hi_a, unsigned char *__restrict__ lo_a,
+                                                 unsigned char *__restrict__ hi_b, unsigned char *__restrict__ lo_b, const uint4 piece_a,
+                                                 const uint4 piece_b, const uint32_t bit0) {
+    const uint32_t wa[4] = {piece_a.x, piece_a.y, piece_a.z, piece_a.w}, wb[4] = {piece_b.x, piece_b.y, piece_b.z, piece_b.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t ah = (wa[q] >> 4) & 0x0F0F0F0Fu, al = wa[q] & 0x0F0F0F0Fu;
+        const uint32_t bh = (wb[q] >> 4) & 0x0F0F0F0Fu, bl = wb[q] & 0x0F0F0F0Fu;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t bit = bit0 * (1u << (4 * q + k));
+            uint32_t *const p0 = reinterpret_cast<uint32_t *>(hi_a + ((ah >> (8 * k)) & 0xFFu) * ESTRIDE);
+            uint32_t *const p1 = reinterpret_cast<uint32_t *>(lo_a + ((al >> (8 * k)) & 0xFFu) * ESTRIDE);
+            uint32_t *const p2 = reinterpret_cast<uint32_t *>(hi_b + ((bh >> (8 * k)) & 0xFFu) * ESTRIDE);
+            uint32_t *const p3 = reinterpret_cast<uint32_t *>(lo_b + ((bl >> (8 * k)) & 0xFFu) * ESTRIDE);
+            // the four addresses are distinct by construction (two tables x two words): load all, then store all
+            const uint32_t v0 = *p0, v1 = *p1, v2 = *p2, v3 = *p3;
+            *p0 = v0 | bit, *p1 = v1 | bit, *p2 = v2 | bit, *p3 = v3 | bit;
+        }
+    }
+}
+
+template <uint32_t ESTRIDE>
+__device__ __forceinline__ void build_piece(unsigned char *__restrict__ hi_a, unsigned char *__restrict__ lo_a, const uint4 piece_a,
+                                            const uint32_t bit0) {
+    const uint32_t wa[4] = {piece_a.x, piece_a.y, piece_a.z, piece_a.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t ah = (wa[q] >> 4) & 0x0F0F0F0Fu, al = wa[q] & 0x0F0F0F0Fu;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t bit = bit0 * (1u << (4 * q + k));
+            uint32_t *const p0 = reinterpret_cast<uint32_t *>(hi_a + ((ah >> (8 * k)) & 0xFFu) * ESTRIDE);
+            uint32_t *const p1 = reinterpret_cast<uint32_t *>(lo_a + ((al >> (8 * k)) & 0xFFu) * ESTRIDE);
+            const uint32_t v0 = *p0, v1 = *p1;
+            *p0 = v0 | bit, *p1 = v1 | bit;
+        }
+    }
+}
+
 // A thread computes any pair whose pattern fits its K words and SKIPS (writes nothing for) a longer one: that is
 // what lets the host launch this kernel speculatively, before the batch's length statistics are known — the
 // statistics then tell the host whether anything was skipped (engine.cu, run_device_batch).
@@ -109,26 +155,27 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
         const uint32_t head = min(m, (uint32_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(pat) & 15u)) & 15u));
         for (; i < head; ++i) add_symbol(s + i, ldg1(pat + i));
         if (((s + i) & 15u) == 0u) {
-            // aligned pieces: 16 symbols share one table word and one 16-bit half of it
-            for (; i + 16 <= m; i += 16) {
-                const uint4 piece = ldg16(pat + i);
-                const uint32_t pos = s + i;
-                unsigned char *const hi_w = tbl_hi + word_offset<K, T>(tid, pos >> 5), *const lo_w = tbl_lo + word_offset<K, T>(tid, pos >> 5);
-                const uint32_t bit0 = 1u << (pos & 16u);
-                const uint32_t w[4] = {piece.x, piece.y, piece.z, piece.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t wh = (w[q] >> 4) & 0x0F0F0F0Fu, wl = w[q] & 0x0F0F0F0Fu;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t bit = bit0 * (1u << (4 * q + k));
-                        uint32_t *hi = reinterpret_cast<uint32_t *>(hi_w + ((wh >> (8 * k)) & 0xFFu) * ESTRIDE);
-                        uint32_t *lo = reinterpret_cast<uint32_t *>(lo_w + ((wl >> (8 * k)) & 0xFFu) * ESTRIDE);
-                        *hi |= bit;
-                        *lo |= bit;
-                    }
+            // Aligned pieces: 16 symbols share one table word and one 16-bit half of it. The pattern is top-aligned,
+            // so the pieces from position s+i up to 32K are all full. Pieces 32 positions apart sit in different
+            // words: they are built in interleaved pairs (four independent shared-memory update chains).
+            const uint32_t p_begin = s + i, p_end = 32u * K;
+#pragma unroll 1
+            for (uint32_t half = 0; half < 32u; half += 16u) {
+                uint32_t pos = (p_begin & ~31u) + half;
+                if (pos < p_begin) pos += 32u;
+                const uint32_t bit0 = 1u << half;
+#pragma unroll 1
+                for (; pos + 32u < p_end; pos += 64u) {
+                    const uint4 piece_a = ldg16(pat + (pos - s)), piece_b = ldg16(pat + (pos + 32u - s));
+                    const uint32_t off_a = word_offset<K, T>(tid, pos >> 5), off_b = word_offset<K, T>(tid, (pos >> 5) + 1u);
+                    build_piece_pair<ESTRIDE>(tbl_hi + off_a, tbl_lo + off_a, tbl_hi + off_b, tbl_lo + off_b, piece_a, piece_b, bit0);
+                }
+                if (pos < p_end) {
+                    const uint32_t off_a = word_offset<K, T>(tid, pos >> 5);
+                    build_piece<ESTRIDE>(tbl_hi + off_a, tbl_lo + off_a, ldg16(pat + (pos - s)), bit0);
                 }
             }
+            i = m;
         } else {
             for (; i + 16 <= m; i += 16) {
                 const uint4 piece = ldg16(pat + i);
