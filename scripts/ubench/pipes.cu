@@ -95,6 +95,51 @@ __global__ void bench(uint32_t *out, uint32_t seed, uint32_t one, uint32_t two, 
                 asm volatile("shf.l.wrap.b32 %0, %1, %0, 1;" : "+r"(d) : "r"(f));
                 asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(g) : "r"(h), "r"(c));
                 asm volatile("shf.l.wrap.b32 %0, %1, %0, 1;" : "+r"(e) : "r"(f));
+            } else if (MODE == 9) { // dp4a x8
+                asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(a) : "r"(two), "r"(c));
+                asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(d) : "r"(two), "r"(f));
+                asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(g) : "r"(two), "r"(c));
+                asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(b) : "r"(two), "r"(f));
+                asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(a) : "r"(two), "r"(c));
+                asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(d) : "r"(two), "r"(f));
+                asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(g) : "r"(two), "r"(c));
+                asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(b) : "r"(two), "r"(f));
+            } else if (MODE == 10) { // 4 LOP3 + 4 dp4a
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(c));
+                asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(d) : "r"(two), "r"(f));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(g) : "r"(h), "r"(c));
+                asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(e) : "r"(two), "r"(f));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(c));
+                asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(d) : "r"(two), "r"(f));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(g) : "r"(h), "r"(c));
+                asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(e) : "r"(two), "r"(f));
+            } else if (MODE == 11) { // 4 LOP3 + 4 IMAD.HI
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(c));
+                asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(d) : "r"(f));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(g) : "r"(h), "r"(c));
+                asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(e) : "r"(f));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(c));
+                asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(d) : "r"(f));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(g) : "r"(h), "r"(c));
+                asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(e) : "r"(f));
+            } else if (MODE == 12) { // 6 LOP3 + 2 IMAD.HI
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(c));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(g) : "r"(h), "r"(c));
+                asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(d) : "r"(f));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b) : "r"(h), "r"(c));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(c));
+                asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(e) : "r"(f));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(g) : "r"(h), "r"(c));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b) : "r"(h), "r"(c));
+            } else if (MODE == 13) { // 6 LOP3 + 2 IMAD
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(c));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(g) : "r"(h), "r"(c));
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(d) : "r"(two), "r"(f));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b) : "r"(h), "r"(c));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(c));
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(e) : "r"(two), "r"(f));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(g) : "r"(h), "r"(c));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b) : "r"(h), "r"(c));
             } else if (MODE == 8) { // 5 LOP3 + 3 IMAD
                 asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(c));
                 asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(d) : "r"(two), "r"(f));
@@ -124,10 +169,11 @@ void run(const char *name, int warps) {
     cudaFree(out); cudaFree(cyc);
 }
 int main() {
-    for (int warps : {4, 8, 16, 32}) {
+    for (int warps : {8, 24}) {
         run<0>("LOP3", warps); run<1>("IMAD", warps); run<2>("IMAD.WIDE(+1 LOP3 each)", warps); run<3>("IMAD.HI", warps);
         run<4>("LOP3:IMAD 4:4", warps); run<5>("LOP3:IMAD.WIDE 6:2 (+2 IADD)", warps); run<6>("IADD", warps);
         run<7>("LOP3:SHF 4:4", warps); run<8>("LOP3:IMAD 5:3", warps);
+        run<9>("DP4A", warps); run<10>("LOP3:DP4A 4:4", warps); run<11>("LOP3:IMAD.HI 4:4", warps); run<12>("LOP3:IMAD.HI 6:2", warps); run<13>("LOP3:IMAD 6:2", warps);
     }
     return 0;
 }

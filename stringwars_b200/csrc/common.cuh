@@ -29,7 +29,14 @@ struct PairView {
     uint64_t out_index;
 };
 
-__device__ __forceinline__ PairView pair_at(const PairSpace &ps, uint64_t slot) {
+// pair_at in two halves, for kernels that request a pair's offsets long before they need them: pair_request issues
+// the four offset loads and does no arithmetic on their results, pair_resolve turns them into a PairView.
+struct PairRequest {
+    uint64_t a0, a1, b0, b1; // raw offsets (in flight until first use)
+    uint64_t out_index;
+};
+
+__device__ __forceinline__ PairRequest pair_request(const PairSpace &ps, uint64_t slot) {
     uint64_t k = ps.order ? (uint64_t)ps.order[slot] : slot;
     uint64_t ia = k, ib = k, oi = k;
     if (ps.n_c) {
@@ -37,16 +44,24 @@ __device__ __forceinline__ PairView pair_at(const PairSpace &ps, uint64_t slot) 
         ib = k - ia * ps.n_c;
         oi = ia * ps.stride + ib;
     }
+    PairRequest r;
+    r.a0 = ps.a_offs[ia], r.a1 = ps.a_offs[ia + 1];
+    r.b0 = ps.b_offs[ib], r.b1 = ps.b_offs[ib + 1];
+    r.out_index = oi;
+    return r;
+}
+
+__device__ __forceinline__ PairView pair_resolve(const PairSpace &ps, const PairRequest &r) {
     PairView v;
-    uint64_t a0 = ps.a_offs[ia], a1 = ps.a_offs[ia + 1];
-    uint64_t b0 = ps.b_offs[ib], b1 = ps.b_offs[ib + 1];
-    v.a = ps.a_data + a0;
-    v.b = ps.b_data + b0;
-    v.la = (uint32_t)((a1 - a0) >> ps.len_shift);
-    v.lb = (uint32_t)((b1 - b0) >> ps.len_shift);
-    v.out_index = oi;
+    v.a = ps.a_data + r.a0;
+    v.b = ps.b_data + r.b0;
+    v.la = (uint32_t)((r.a1 - r.a0) >> ps.len_shift);
+    v.lb = (uint32_t)((r.b1 - r.b0) >> ps.len_shift);
+    v.out_index = r.out_index;
     return v;
 }
+
+__device__ __forceinline__ PairView pair_at(const PairSpace &ps, uint64_t slot) { return pair_resolve(ps, pair_request(ps, slot)); }
 
 // Read-only 16-byte / 4-byte / 1-byte global loads (LDG through the non-coherent path).
 __device__ __forceinline__ uint4 ldg16(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }

@@ -1,33 +1,37 @@
 // lev_bitpar.cuh — unit-cost Levenshtein by the Myers (1999) / Hyyrö (2003) bit-vector recurrence, sm_100a.
 //
 // Why this exists next to the wavefront kernel: with unit costs the vertical/horizontal DP deltas are in
-// {-1, 0, +1}, so 32 DP rows fit two 32-bit masks and one column step costs ~10 LOP3/SHF per 32 cells
+// {-1, 0, +1}, so 32 DP rows fit two 32-bit masks and one column step costs ~9 integer ops per 32 cells
 // instead of ~4-5 integer instructions per cell. Integer ALU issue is the binding roofline of this path
-// (DESIGN.md §5), so this is the kernel that moves the HBM-roofline fraction.
+// (DESIGN.md §4), so this is the kernel that moves the HBM-roofline fraction.
 //
 // Mapping: one THREAD per pair, K 32-bit words of vertical state (pattern = the shorter string, <= 32*K
 // symbols). The match mask Eq(c) is never stored for 256 symbols (2 KB/word would kill occupancy): it is
 // rebuilt per column from two 16-entry nibble tables, Eq(c) = HI[c >> 4] & LO[c & 15], because a pattern
-// byte equals c iff both nibbles do. The tables live in shared memory, laid out [table][nibble][thread][K]
-// so a warp's lookups are one conflict-free LDS.32/64/128 each. Bytes stream straight from HBM with
-// aligned 16-byte read-only loads, one piece prefetched (thread-private strings: nothing to share, so no
-// smem staging here — the group-per-pair wavefront kernel is the one that stages).
+// byte equals c iff both nibbles do. The tables live in shared memory (NibbleTables below). Bytes stream
+// straight from HBM with aligned 16-byte read-only loads, one piece prefetched (thread-private strings: nothing
+// to share, so no smem staging here — the group-per-pair wavefront kernel is the one that stages).
 //
-// Instruction-level design (the kernel is ALU-pipe bound, ncu: profiles/r1_*):
+// Instruction-level design. The kernel is bound by the ALU pipe (LOP3 / SHF / IADD3: one warp instruction per two
+// cycles per scheduler); measured on a B200 (scripts/ubench/): the FMA pipe (IMAD, IDP.4A) issues beside it at
+// the same rate, IMAD.WIDE / IMAD.HI run at a quarter rate and stall the ALU stream, so they are avoided.
 //  * The pattern is TOP-aligned: symbol i sits at bit s+i, s = 32K-m. The s rows below it are "free" rows
 //    (vertical delta 0, never matching) that replicate DP row 0, so the result is unchanged and no bit index
 //    depends on m at run time.
 //  * The distance is not tracked per column at all: D[m][n] = n + popc(Pv) - popc(Mv) of the final column.
-//  * `x << 1 | carry` is written as x*2+carry and the adds as mul-adds: they issue on the FMA pipe (IMAD),
-//    which is otherwise idle, instead of the saturated ALU pipe.
-//  * Symbols are nibble-split four at a time ((w >> 4) & 0x0F0F0F0F, w & 0x0F0F0F0F); a table address is one
-//    byte extract plus one IMAD.
+//  * Hyyrö's single-mask form, D0 = (((Eq & Pv) + Pv) ^ Pv) | Eq | Mv, over the whole 32K-bit column: 7 LOP3 per
+//    word (Eq = HI & LO only ever appears inside 3-input LOP3s), one carry chain for the add, one funnel shift per
+//    shifted word above word 0 (column_step).
+//  * A table address is ONE instruction: the four symbols of a text word are nibble-split together
+//    (w & 0x0F0F0F0F, (w >> 4) & 0x0F0F0F0F) and IDP.4A with a one-hot byte selector of 128 computes
+//    base + nibble * 128 — which is why a table entry row is 128 bytes.
+//  * The table build is 16-bit read-modify-writes in up to eight independent chains, lanes rotated over the words so
+//    that no two lanes of a warp meet in a bank (build_pieces).
 //
 // Parity: bit-exact with the CPU oracle (both of its algorithm families), the restatement of
 // `rapidfuzz::distance::levenshtein::distance` as called at StringWars similarities/bench.rs:416-419.
 #pragma once
 #include "common.cuh"
-#include <type_traits>
 
 namespace swb {
 
@@ -39,25 +43,31 @@ __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
     asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
     return r;
 }
-// x * mul + carry_in as one 64-bit multiply-add (IMAD.WIDE.U32, FMA pipe): with mul = 2 the low half is
-// (x << 1) | carry_in and the high half is the bit that left the word = the carry into the next word. `mul` is
-// a run-time value the assembler cannot see through, otherwise ptxas rewrites the multiply into ALU-pipe
-// LEA / LEA.HI.X / SHF, and the ALU pipe is the one this kernel saturates.
-__device__ __forceinline__ void mad_wide(uint32_t x, uint32_t mul, uint32_t carry_in, uint32_t &lo, uint32_t &hi) {
-    uint64_t r;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(x), "r"(mul), "l"((uint64_t)carry_in));
-    lo = (uint32_t)r, hi = (uint32_t)(r >> 32);
-}
-__device__ __forceinline__ void mul_wide(uint32_t x, uint32_t mul, uint32_t &lo, uint32_t &hi) {
-    uint64_t r;
-    asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(x), "r"(mul));
-    lo = (uint32_t)r, hi = (uint32_t)(r >> 32);
-}
+// x * mul + add as one IMAD (FMA pipe). Callers pass `mul` as a run-time value the assembler cannot see through:
+// with an immediate power of two ptxas rewrites the multiply into ALU-pipe LEA / SHF, the pipe this kernel saturates.
 __device__ __forceinline__ uint32_t mad_lo(uint32_t x, uint32_t mul, uint32_t add) {
     uint32_t r;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(mul), "r"(add));
     return r;
 }
+// sum of byte_i(a) * byte_i(b) + c (IDP.4A, FMA pipe, full rate).
+__device__ __forceinline__ uint32_t dp4a(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
 // sum = a + b over K 32-bit words (little-endian), one carry chain.
 template <int K>
@@ -85,17 +95,31 @@ struct BitparConfig {
     static constexpr int THREADS = K <= 4 ? 128 : 64; // 128 * K bytes of tables per thread
 };
 
-// Byte offset of word w of THIS thread inside a table entry. K <= 4: the thread's K words are contiguous
-// ([thread][K]); K = 8: two 4-word parts, each part [thread][4], so that every LDS.128 of a warp covers 512
-// contiguous bytes (a [thread][8] layout would put 32-byte strides under 16-byte loads: 2-way bank conflicts).
+// Shared-memory layout of the nibble tables of a block of T threads with K words each.
+// A thread's K words are split into PARTS parts of at most 4 words (one LDS.32/64/128 each); a ROW is the 128
+// bytes that TPR consecutive threads' slots of one part make, and an entry of a table is one row:
+//     [group of TPR threads][part][table HI|LO][16 entries][TPR threads][SB bytes]
+// so (a) a warp's lookup is conflict-free (each quarter/half/full warp reads one contiguous row per wavefront),
+// and (b) the address of entry n is base + n * 128: one IDP.4A from a packed nibble word.
 template <int K, int T>
-__device__ __forceinline__ uint32_t word_offset(int tid, uint32_t w) {
-    if constexpr (K <= 4) return (uint32_t)tid * (K * 4) + w * 4u;
-    else return (w >> 2) * (T * 16u) + (uint32_t)tid * 16u + (w & 3u) * 4u;
-}
+struct NibbleTables {
+    static constexpr int PARTS = K <= 4 ? 1 : K / 4;
+    static constexpr int SB = (K < 4 ? K : 4) * 4; // slot bytes per thread and part
+    static constexpr int TPR = 128 / SB;           // threads per row
+    static constexpr uint32_t ROW = 128, TABLE = 16 * ROW;
+    static constexpr uint32_t PART_STRIDE = 2 * TABLE;
+    static constexpr uint32_t BYTES = (uint32_t)T * K * 4 * 32;
+    // lanes of a warp whose slots share a bank (they differ only in the group): the build rotates them over words
+    static constexpr uint32_t SHARERS = 32 / TPR;
+    // shared address of this thread's part-0 slot in entry 0 of the HI table; LO is + TABLE, part p is + p * PART_STRIDE
+    __device__ static __forceinline__ uint32_t base(uint32_t smem, int tid) {
+        return smem + (uint32_t)(tid / TPR) * (PARTS * PART_STRIDE) + (uint32_t)(tid % TPR) * SB;
+    }
+    // byte offset of word w inside the thread's slots (relative to base)
+    __device__ static __forceinline__ uint32_t word(uint32_t w) { return (w >> 2) * PART_STRIDE + (w & 3u) * 4u; }
+};
 
-// K table words of THIS thread from the entry at 32-bit shared-space address `addr` (entry base + the thread's
-// word_offset): explicit ld.shared so the address is one 32-bit register plus an immediate.
+// K table words of THIS thread from the entry row at 32-bit shared-space address `addr` (base + n * 128).
 template <int K, int T>
 __device__ __forceinline__ void load_words(uint32_t addr, uint32_t (&w)[K]) {
     if constexpr (K == 1) {
@@ -105,74 +129,124 @@ __device__ __forceinline__ void load_words(uint32_t addr, uint32_t (&w)[K]) {
     } else {
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
         if constexpr (K == 8)
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(addr), "n"(T * 16));
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];"
+                         : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                         : "r"(addr), "n"(NibbleTables<K, T>::PART_STRIDE));
     }
 }
-// Same through a generic pointer to the entry (lev_bitpar_cross.cuh).
+
+// Zero this thread's 32 x K table words.
 template <int K, int T>
-__device__ __forceinline__ void load_words(const unsigned char *entry, int tid, uint32_t (&w)[K]) {
-    load_words<K, T>((uint32_t)__cvta_generic_to_shared(entry) + word_offset<K, T>(tid, 0), w);
+__device__ __forceinline__ void zero_tables(uint32_t base) {
+    using NT = NibbleTables<K, T>;
+#pragma unroll
+    for (int p = 0; p < NT::PARTS; ++p)
+#pragma unroll 8
+        for (int e = 0; e < 32; ++e) { // 16 HI rows, then 16 LO rows
+            const uint32_t addr = base + p * NT::PART_STRIDE + e * NT::ROW;
+            if constexpr (K == 1) asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(0u) : "memory");
+            else if constexpr (K == 2) asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(addr), "r"(0u) : "memory");
+            else asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+        }
+}
+
+// One DP column: Hyyrö's single-mask form of the recurrence over the whole 32K-bit column at once.
+// D0 = (((Eq & Pv) + Pv) ^ Pv) | Eq | Mv marks the cells whose diagonal delta is 0 and replaces both of Myers' Xv and
+// Xh, so Eq = HI & LO is never materialised (it only appears inside two 3-input LOP3s): 7 logic ops per word. The
+// add is ONE 32K-bit add (a carry chain, 1 op per word) instead of Myers' per-word blocks, so no word waits for the
+// deltas of the word above it and no block carry has to be folded into Eq. Shifted deltas: word 0 takes the
+// horizontal delta of DP row 0 (+1) as x * 2 + 1 / x * 2 (IMAD, FMA pipe); the words above take the bit leaving
+// the word below through one funnel shift (SHF.L.W). `one`, `two`: run-time 1 and 2 (see mad_lo).
+template <int K>
+__device__ __forceinline__ void column_step(const uint32_t (&hi)[K], const uint32_t (&lo)[K], uint32_t (&Pv)[K], uint32_t (&Mv)[K],
+                                            uint32_t one, uint32_t two) {
+    uint32_t t[K], x[K], sum[K];
+#pragma unroll
+    for (int w = 0; w < K; ++w) {
+        t[w] = lop3<0x80>(hi[w], lo[w], Pv[w]); // Eq & Pv
+        x[w] = lop3<0xEA>(hi[w], lo[w], Mv[w]); // Eq | Mv
+    }
+    add_wide<K>(t, Pv, sum, one);
+    uint32_t ph_below = 0u, mh_below = 0u;
+#pragma unroll
+    for (int w = 0; w < K; ++w) {
+        const uint32_t d0 = lop3<0xBE>(sum[w], Pv[w], x[w]); // ((t + Pv) ^ Pv) | x
+        const uint32_t ph = lop3<0xF1>(Mv[w], d0, Pv[w]);    // Mv | ~(D0 | Pv)
+        const uint32_t mh = Pv[w] & d0;
+        const uint32_t phs = w == 0 ? mad_lo(ph, two, one) : __funnelshift_l(ph_below, ph, 1);
+        const uint32_t mhs = w == 0 ? mad_lo(mh, two, 0u) : __funnelshift_l(mh_below, mh, 1);
+        ph_below = ph, mh_below = mh;
+        Pv[w] = lop3<0xF1>(mhs, d0, phs); // Mh' | ~(D0 | Ph')
+        Mv[w] = phs & d0;
+    }
+}
+
+// Column 0 of the DP matrix for a top-aligned pattern of m = 32K - s rows: rows below the pattern (bit < s) carry
+// vertical delta 0, pattern rows +1.
+template <int K>
+__device__ __forceinline__ void first_column(uint32_t s, uint32_t (&Pv)[K], uint32_t (&Mv)[K]) {
+#pragma unroll
+    for (int w = 0; w < K; ++w) {
+        const uint32_t lo_bit = 32u * w;
+        Pv[w] = s >= lo_bit + 32u ? 0u : (s <= lo_bit ? 0xFFFFFFFFu : 0xFFFFFFFFu << (s - lo_bit));
+        Mv[w] = 0u;
+    }
+}
+
+// The four symbols of a 32-bit word, nibble-split: byte k of `hi` / `lo` is the high / low nibble of symbol k.
+struct NibbleWord {
+    uint32_t hi, lo;
+};
+__device__ __forceinline__ NibbleWord split_nibbles(uint32_t word) { return {(word >> 4) & 0x0F0F0F0Fu, word & 0x0F0F0F0Fu}; }
+// Address of the entry row selected by byte KB of a packed nibble word: base + nibble * 128 (one IDP.4A).
+template <int KB>
+__device__ __forceinline__ uint32_t row_of(uint32_t nibbles, uint32_t base) {
+    return dp4a(nibbles, 128u << (8 * KB), base);
 }
 
 // Table build for aligned 16-symbol pieces. A piece fills one 16-bit half of one table word; per symbol and table it
-// is one read-modify-write of shared memory: AND (isolate the nibble), IMAD (scale it by the entry stride and add
-// the table base), LDS, add the position bit (each position bit is set exactly once per table, so OR == ADD and
-// the add can issue on either pipe), STS. `BuildMul` carries the run-time multipliers (see the column loop: with
-// immediates ptxas turns these IMADs into ALU-pipe LEAs).
-struct BuildMul {
-    uint32_t mul0, mul4, mul8, two; // 2^E, 2^(E-4), 2^(E-8) for nibbles at bit 0, 4, 8; and 2
-};
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-
-// Shared addresses of the entries selected by the 4 symbols of one 32-bit pattern word: hi[k] in the HI table
-// (based at base_hi), lo[k] in the LO table (based at base_lo).
-__device__ __forceinline__ void symbol_slots(uint32_t word, uint32_t base_hi, uint32_t base_lo, const BuildMul &bm, uint32_t (&hi)[4],
-                                             uint32_t (&lo)[4]) {
-    const uint32_t w12 = __umulhi(word, 1u << 20), w24 = __umulhi(word, 1u << 8); // word >> 12, word >> 24 (IMAD.HI)
-    hi[0] = mad_lo(word & 0xF0u, bm.mul4, base_hi), lo[0] = mad_lo(word & 0xFu, bm.mul0, base_lo);
-    hi[1] = mad_lo(w12 & 0xFu, bm.mul0, base_hi), lo[1] = mad_lo(word & 0xF00u, bm.mul8, base_lo);
-    hi[2] = mad_lo(w12 & 0xF00u, bm.mul8, base_hi), lo[2] = mad_lo(w12 & 0xF0u, bm.mul4, base_lo);
-    hi[3] = mad_lo(w24 & 0xF0u, bm.mul4, base_hi), lo[3] = mad_lo(w24 & 0xFu, bm.mul0, base_lo);
-}
-
-// Two pieces that live in DIFFERENT table words: four read-modify-write chains that can never touch the same
-// address (two tables x two words), so each symbol step loads all four words first and stores them afterwards.
-// base_*: shared address of this thread's word in entry 0 of the HI / LO table, for piece a and piece b.
-__device__ __forceinline__ void build_piece_pair(uint32_t hi_a, uint32_t lo_a, uint32_t hi_b, uint32_t lo_b, const uint4 piece_a,
-                                                 const uint4 piece_b, uint32_t bit, const BuildMul &bm) {
-    const uint32_t wa[4] = {piece_a.x, piece_a.y, piece_a.z, piece_a.w}, wb[4] = {piece_b.x, piece_b.y, piece_b.z, piece_b.w};
+// is one 16-bit read-modify-write of shared memory: IDP.4A (entry address), LDS.U16, add the position bit (each
+// position bit is set exactly once per table, so OR == ADD), STS.U16. Pieces of different words or different
+// halves can never touch the same address, so NP pieces are 2*NP independent update chains: each symbol step loads
+// all 2*NP half-words first and stores them afterwards (four pieces = the whole pattern at K = 2 = eight chains,
+// 16 dependent steps instead of 64).
+// hi_base[p]: shared address of the 16-bit half piece p fills, in entry 0 of the HI table (LO is + table_bytes).
+template <int NP>
+__device__ __forceinline__ void build_pieces(const uint32_t (&hi_base)[NP], const uint4 (&piece)[NP], uint32_t table_bytes) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        uint32_t ah[4], al[4], bh[4], bl[4];
-        symbol_slots(wa[q], hi_a, lo_a, bm, ah, al);
-        symbol_slots(wb[q], hi_b, lo_b, bm, bh, bl);
+        NibbleWord nw[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) nw[p] = split_nibbles(q == 0 ? piece[p].x : (q == 1 ? piece[p].y : (q == 2 ? piece[p].z : piece[p].w)));
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const uint32_t v0 = lds32(ah[k]), v1 = lds32(al[k]), v2 = lds32(bh[k]), v3 = lds32(bl[k]);
-            sts32(ah[k], v0 + bit), sts32(al[k], v1 + bit), sts32(bh[k], v2 + bit), sts32(bl[k], v3 + bit);
-            bit = mad_lo(bit, bm.two, 0u);
+            uint32_t ah[NP], al[NP], vh[NP], vl[NP];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const uint32_t lo_base = hi_base[p] + table_bytes;
+                if (k == 0) ah[p] = row_of<0>(nw[p].hi, hi_base[p]), al[p] = row_of<0>(nw[p].lo, lo_base);
+                if (k == 1) ah[p] = row_of<1>(nw[p].hi, hi_base[p]), al[p] = row_of<1>(nw[p].lo, lo_base);
+                if (k == 2) ah[p] = row_of<2>(nw[p].hi, hi_base[p]), al[p] = row_of<2>(nw[p].lo, lo_base);
+                if (k == 3) ah[p] = row_of<3>(nw[p].hi, hi_base[p]), al[p] = row_of<3>(nw[p].lo, lo_base);
+            }
+#pragma unroll
+            for (int p = 0; p < NP; ++p) vh[p] = lds16(ah[p]), vl[p] = lds16(al[p]);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) sts16(ah[p], vh[p] + (1u << (4 * q + k))), sts16(al[p], vl[p] + (1u << (4 * q + k)));
         }
     }
 }
 
-__device__ __forceinline__ void build_piece(uint32_t hi_a, uint32_t lo_a, const uint4 piece_a, uint32_t bit, const BuildMul &bm) {
-    const uint32_t wa[4] = {piece_a.x, piece_a.y, piece_a.z, piece_a.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        uint32_t ah[4], al[4];
-        symbol_slots(wa[q], hi_a, lo_a, bm, ah, al);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t v0 = lds32(ah[k]), v1 = lds32(al[k]);
-            sts32(ah[k], v0 + bit), sts32(al[k], v1 + bit);
-            bit = mad_lo(bit, bm.two, 0u);
-        }
-    }
+// One symbol into the tables (ragged heads and tails, unaligned patterns): bit `pos` of HI[c >> 4] and LO[c & 15].
+template <int K, int T>
+__device__ __forceinline__ void add_symbol(uint32_t base, uint32_t pos, uint32_t c) {
+    using NT = NibbleTables<K, T>;
+    const uint32_t bit = 1u << (pos & 31u);
+    const uint32_t ah = base + NT::word(pos >> 5) + (c >> 4) * NT::ROW, al = base + NT::TABLE + NT::word(pos >> 5) + (c & 15u) * NT::ROW;
+    const uint32_t vh = lds32(ah);
+    sts32(ah, vh | bit);
+    const uint32_t vl = lds32(al);
+    sts32(al, vl | bit);
 }
 
 // A thread computes any pair whose pattern fits its K words and SKIPS (writes nothing for) a longer one: that is
@@ -181,34 +255,17 @@ __device__ __forceinline__ void build_piece(uint32_t hi_a, uint32_t lo_a, const 
 template <int K>
 __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(PairSpace ps, uint64_t begin, uint64_t count) {
     constexpr int T = BitparConfig<K>::THREADS;
-    constexpr uint32_t ESTRIDE = T * K * 4; // bytes between consecutive table entries
-    extern __shared__ __align__(16) unsigned char tbl_bytes[]; // [32 entries][T][K] u32
+    using NT = NibbleTables<K, T>;
+    extern __shared__ __align__(16) unsigned char tbl_bytes[]; // NibbleTables<K, T>::BYTES
     const int tid = threadIdx.x;
     const uint64_t local = (uint64_t)blockIdx.x * T + tid;
-    unsigned char *const tbl_hi = tbl_bytes, *const tbl_lo = tbl_bytes + 16 * ESTRIDE;
-    // 1, 2 and the nibble scales as values ptxas cannot fold (count < 2^63 always): with immediates it rewrites the
-    // multiply-adds below into ALU-pipe LEA / SHF, and the ALU pipe is the one this kernel saturates.
+    if (local >= count) return;
+    // 1 and 2 as values ptxas cannot fold (count < 2^63 always): see mad_lo
     const uint32_t opaque0 = (uint32_t)(count >> 63);
     const uint32_t one = 1u + opaque0, two = 2u + opaque0;
-    constexpr int E = K == 1 ? 9 : (K == 2 ? 10 : 11);
-    static_assert(ESTRIDE == (1u << E), "nibble offsets assume a power-of-two entry stride");
-    const BuildMul bm = {(1u << E) + opaque0, (1u << (E - 4)) + opaque0, (1u << (E - 8)) + opaque0, two};
-    const uint32_t tbl_s = (uint32_t)__cvta_generic_to_shared(tbl_bytes);
-    const uint32_t base_hi = tbl_s + word_offset<K, T>(tid, 0), base_lo = base_hi + 16u * ESTRIDE;
+    const uint32_t base_hi = NT::base((uint32_t)__cvta_generic_to_shared(tbl_bytes), tid), base_lo = base_hi + NT::TABLE;
 
-    // The pair's offsets are requested first; the table zeroing below runs while they are in flight.
-    const bool live = local < count;
-    PairView pv = {nullptr, nullptr, 0u, 0u, 0u};
-    if (live) pv = pair_at(ps, begin + local);
-
-    // Zero this thread's 32 x K table words.
-#pragma unroll 8
-    for (int e = 0; e < 32; ++e) {
-#pragma unroll
-        for (int w = 0; w < K; ++w) *reinterpret_cast<uint32_t *>(tbl_bytes + e * ESTRIDE + word_offset<K, T>(tid, w)) = 0u;
-    }
-    if (!live) return;
-
+    const PairView pv = pair_at(ps, begin + local);
     // pattern = shorter string (distance is symmetric), text = longer one
     const bool swap = pv.la > pv.lb;
     const uint8_t *pat = swap ? pv.b : pv.a;
@@ -222,46 +279,77 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
     if (m > 32u * K) return; // not this kernel's class (speculative launch on a batch that changed shape)
     const uint32_t s = 32u * K - m; // pattern symbol i lives at bit position s + i
 
-    // ---- build the nibble tables: bit p of HI[h] (LO[l]) is set iff the symbol at position p has high (low) nibble h (l)
-    auto add_symbol = [&](uint32_t pos, uint32_t c) {
-        const uint32_t bit = 1u << (pos & 31u);
-        const uint32_t word_off = word_offset<K, T>(tid, pos >> 5);
-        uint32_t *hi = reinterpret_cast<uint32_t *>(tbl_hi + (c >> 4) * ESTRIDE + word_off);
-        uint32_t *lo = reinterpret_cast<uint32_t *>(tbl_lo + (c & 15u) * ESTRIDE + word_off);
-        *hi |= bit;
-        *lo |= bit;
+    // ---- requests that can leave before the tables are zeroed
+    // Pattern: bytes up to the first 16-byte boundary one by one; from there, if the table position is 16-aligned too,
+    // aligned pieces: 16 symbols share one table word and one 16-bit half of it, and because the pattern is
+    // top-aligned every piece from position p_begin up to 32K is full. The table is built a QUAD at a time: the
+    // four pieces of words a and a+1 (64 pattern bytes). Lanes whose slots share a bank (NT::SHARERS of them per
+    // warp) start at different words: lane group g works on words (2q + g) % K and +1 while group 0 works on words
+    // 2q and 2q+1, so in a batch of equal lengths every access of the build is conflict-free.
+    const uint32_t pat_head = min(m, (uint32_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(pat) & 15u)) & 15u));
+    const bool pieces = ((s + pat_head) & 15u) == 0u;
+    const uint32_t p_begin = s + pat_head;
+    constexpr uint32_t NQ = (K + 1) / 2; // quads
+    constexpr int QP = K == 1 ? 2 : 4;   // pieces per quad
+    const uint32_t g = NT::SHARERS == 1 ? 0u : ((uint32_t)tid / NT::TPR) % NT::SHARERS;
+    // piece p of quad q: word (2q + g + p/2) % K, half p % 2
+    auto piece_pos = [&](uint32_t q, int p) -> uint32_t { return 32u * ((2u * q + g + (uint32_t)(p >> 1)) % K) + 16u * (uint32_t)(p & 1); };
+    auto load_quad = [&](uint32_t q, uint4 (&pc)[QP]) {
+#pragma unroll
+        for (int p = 0; p < QP; ++p) {
+            const uint32_t pos = piece_pos(q, p);
+            if (pos >= p_begin) pc[p] = ldg16(pat + (pos - s));
+        }
     };
+    auto build_quad = [&](uint32_t q, const uint4 (&pc)[QP]) {
+        uint32_t hb[QP];
+        bool all = true;
+#pragma unroll
+        for (int p = 0; p < QP; ++p) {
+            const uint32_t pos = piece_pos(q, p);
+            hb[p] = base_hi + NT::word(pos >> 5) + ((pos >> 3) & 2u);
+            all = all && pos >= p_begin;
+        }
+        if (all) {
+            build_pieces<QP>(hb, pc, NT::TABLE);
+        } else {
+#pragma unroll 1
+            for (int p = 0; p < QP; ++p) {
+                if (piece_pos(q, p) < p_begin) continue;
+                // dynamic p: select the piece and its base without indexing the register arrays
+                uint4 one_pc[1] = {pc[0]};
+                uint32_t one_hb[1] = {hb[0]};
+#pragma unroll
+                for (int r = 1; r < QP; ++r)
+                    if (p == r) one_pc[0] = pc[r], one_hb[0] = hb[r];
+                build_pieces<1>(one_hb, one_pc, NT::TABLE);
+            }
+        }
+    };
+    uint4 quad_a[QP], quad_b[QP];
+#pragma unroll
+    for (int p = 0; p < QP; ++p) quad_a[p] = quad_b[p] = make_uint4(0, 0, 0, 0);
+    if (pieces) load_quad(0, quad_a);
+    // Text: bytes up to the first 16-byte boundary one by one, then aligned pieces, one piece prefetched.
+    const uint32_t txt_head = min(n, (uint32_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(txt) & 15u)) & 15u));
+    uint4 txt_nxt = make_uint4(0, 0, 0, 0);
+    if (txt_head + 16u <= n) txt_nxt = ldg16(txt + txt_head);
+
+    zero_tables<K, T>(base_hi);
+
+    // ---- build the nibble tables: bit p of HI[h] (LO[l]) is set iff the symbol at position p has high (low) nibble h (l)
     {
         uint32_t i = 0;
-        const uint32_t head = min(m, (uint32_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(pat) & 15u)) & 15u));
-        for (; i < head; ++i) add_symbol(s + i, ldg1(pat + i));
-        if (((s + i) & 15u) == 0u) {
-            // Aligned pieces: 16 symbols share one table word and one 16-bit half of it. The pattern is top-aligned,
-            // so every piece from position p_begin up to 32K is full. Pieces are built two at a time, one from word a
-            // and one from word a+1 (four independent update chains), and the lanes of a warp start at DIFFERENT
-            // words: with [thread][K] slots a warp's 32-bit accesses to one word index hit only 32/K' banks (K' =
-            // min(K, 4) lanes share a bank), so lane group g = (lane / (32/K')) % K' works on word (2i + g) % K while
-            // group 0 works on word 2i. In a batch of equal lengths every table access is then conflict-free.
-            const uint32_t p_begin = s + i;
-            constexpr uint32_t KP = K < 4 ? K : 4;
-            const uint32_t g = KP == 1 ? 0u : ((uint32_t)tid / (32u / KP)) % KP;
+        for (; i < pat_head; ++i) add_symbol<K, T>(base_hi, s + i, ldg1(pat + i));
+        if (pieces) {
+            // the next quad's pieces are in flight while the current quad is built (two buffers, no moves)
 #pragma unroll 1
-            for (uint32_t it = 0; it < (K + 1) / 2; ++it) {
-                const uint32_t wa = (2u * it + g) % K, wb = (wa + 1u) % K;
-                const uint32_t off_a = word_offset<K, T>(0, wa), off_b = word_offset<K, T>(0, wb);
-#pragma unroll 1
-                for (uint32_t half = 0; half < 32u; half += 16u) {
-                    const uint32_t pos_a = 32u * wa + half, pos_b = 32u * wb + half;
-                    const bool act_a = pos_a >= p_begin, act_b = K > 1 && pos_b >= p_begin;
-                    const uint32_t bit0 = 1u << half;
-                    if (act_a && act_b) {
-                        const uint4 piece_a = ldg16(pat + (pos_a - s)), piece_b = ldg16(pat + (pos_b - s));
-                        build_piece_pair(base_hi + off_a, base_lo + off_a, base_hi + off_b, base_lo + off_b, piece_a, piece_b, bit0, bm);
-                    } else if (act_a) {
-                        build_piece(base_hi + off_a, base_lo + off_a, ldg16(pat + (pos_a - s)), bit0, bm);
-                    } else if (act_b) {
-                        build_piece(base_hi + off_b, base_lo + off_b, ldg16(pat + (pos_b - s)), bit0, bm);
-                    }
+            for (uint32_t q = 0; q < NQ; q += 2) {
+                if (q + 1 < NQ) load_quad(q + 1, quad_b);
+                build_quad(q, quad_a);
+                if (q + 1 < NQ) {
+                    if (q + 2 < NQ) load_quad(q + 2, quad_a);
+                    build_quad(q + 1, quad_b);
                 }
             }
             i = m;
@@ -272,90 +360,43 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) add_symbol(s + i + 4 * q + k, (w[q] >> (8 * k)) & 0xFFu);
+                    for (int k = 0; k < 4; ++k) add_symbol<K, T>(base_hi, s + i + 4 * q + k, (w[q] >> (8 * k)) & 0xFFu);
             }
         }
-        for (; i < m; ++i) add_symbol(s + i, ldg1(pat + i));
+        for (; i < m; ++i) add_symbol<K, T>(base_hi, s + i, ldg1(pat + i));
     }
 
-    // ---- column loop
+    // ---- column loop. No score is tracked per column: D[m][n] = D[0][n] + (sum of the vertical deltas of column n)
+    //                                                            = n + popc(Pv) - popc(Mv) at the end.
     uint32_t Pv[K], Mv[K];
-#pragma unroll
-    for (int w = 0; w < K; ++w) {
-        // rows below the pattern (bit < s): vertical delta 0; pattern rows: +1 (column 0 of the DP matrix)
-        const uint32_t lo_bit = 32u * w;
-        Pv[w] = s >= lo_bit + 32u ? 0u : (s <= lo_bit ? 0xFFFFFFFFu : 0xFFFFFFFFu << (s - lo_bit));
-        Mv[w] = 0u;
-    }
-    // No score is tracked per column: D[m][n] = D[0][n] + (sum of the vertical deltas of column n)
-    //                                          = n + popc(Pv) - popc(Mv) at the end (free rows carry delta 0).
-    // Hyyro's single-mask form of the recurrence over the whole 32K-bit column at once:
-    // D0 = (((Eq & Pv) + Pv) ^ Pv) | Eq | Mv marks the cells whose diagonal delta is 0 and replaces both of Myers'
-    // Xv and Xh, so Eq = HI & LO is never materialised (it only appears inside two 3-input LOP3s): 7 logic ops per
-    // word. The add is ONE 32K-bit add (a carry chain, 1 op per word) instead of Myers' per-word blocks, so no
-    // word waits for the deltas of the word above it and no block carry has to be folded into Eq.
-    auto step = [&](uint32_t addr_h, uint32_t addr_l) {
-        uint32_t hi[K], lo[K], t[K], x[K], sum[K];
-        load_words<K, T>(addr_h, hi);
-        load_words<K, T>(addr_l, lo);
-#pragma unroll
-        for (int w = 0; w < K; ++w) {
-            t[w] = lop3<0x80>(hi[w], lo[w], Pv[w]); // Eq & Pv
-            x[w] = lop3<0xEA>(hi[w], lo[w], Mv[w]); // Eq | Mv
-        }
-        add_wide<K>(t, Pv, sum, one);
-        uint32_t ph_below = 0u, mh_below = 0u;
-#pragma unroll
-        for (int w = 0; w < K; ++w) {
-            const uint32_t d0 = lop3<0xBE>(sum[w], Pv[w], x[w]); // ((t + Pv) ^ Pv) | x
-            const uint32_t ph = lop3<0xF1>(Mv[w], d0, Pv[w]);    // Mv | ~(D0 | Pv)
-            const uint32_t mh = Pv[w] & d0;
-            // shifted deltas: word 0 takes the horizontal delta of DP row 0 (+1) as x * 2 + 1 / x * 2 (IMAD, FMA pipe);
-            // the words above take the bit leaving the word below through one funnel shift (SHF.L.W)
-            const uint32_t phs = w == 0 ? mad_lo(ph, two, one) : __funnelshift_l(ph_below, ph, 1);
-            const uint32_t mhs = w == 0 ? mad_lo(mh, two, 0u) : __funnelshift_l(mh_below, mh, 1);
-            ph_below = ph, mh_below = mh;
-            Pv[w] = lop3<0xF1>(mhs, d0, phs); // Mh' | ~(D0 | Ph')
-            Mv[w] = phs & d0;
-        }
+    first_column<K>(s, Pv, Mv);
+    auto step = [&](uint32_t row_h, uint32_t row_l) {
+        uint32_t hi[K], lo[K];
+        load_words<K, T>(row_h, hi);
+        load_words<K, T>(row_l, lo);
+        column_step<K>(hi, lo, Pv, Mv, one, two);
     };
-    // Shared address of this thread's words in the table entry selected by the nibble at bit P (P = 0, 4, 8) of
-    // `word`: base + ((word >> P) & 15) * ESTRIDE = one AND (the only ALU-pipe op) and one IMAD that scales the
-    // isolated nibble by 2^(E-P) and adds the base. The multipliers are run-time values so that ptxas keeps the
-    // IMAD (with an immediate it emits LEA, ALU pipe). Nibbles above bit 11 are first brought down by two
-    // multiply-high shifts per 32-bit word (word >> 12, word >> 24: IMAD.HI, FMA pipe).
-    const uint32_t mul0 = bm.mul0, mul4 = bm.mul4, mul8 = bm.mul8;
     auto step4 = [&](uint32_t word) {
-        const uint32_t w12 = __umulhi(word, 1u << 20), w24 = __umulhi(word, 1u << 8); // word >> 12, word >> 24
-        step(mad_lo(word & 0xF0u, mul4, base_hi), mad_lo(word & 0xFu, mul0, base_lo));
-        step(mad_lo(w12 & 0xFu, mul0, base_hi), mad_lo(word & 0xF00u, mul8, base_lo));
-        step(mad_lo(w12 & 0xF00u, mul8, base_hi), mad_lo(w12 & 0xF0u, mul4, base_lo));
-        step(mad_lo(w24 & 0xF0u, mul4, base_hi), mad_lo(w24 & 0xFu, mul0, base_lo));
+        const NibbleWord nw = split_nibbles(word);
+        step(row_of<0>(nw.hi, base_hi), row_of<0>(nw.lo, base_lo));
+        step(row_of<1>(nw.hi, base_hi), row_of<1>(nw.lo, base_lo));
+        step(row_of<2>(nw.hi, base_hi), row_of<2>(nw.lo, base_lo));
+        step(row_of<3>(nw.hi, base_hi), row_of<3>(nw.lo, base_lo));
     };
-    auto step1 = [&](uint32_t c) { step(base_hi + (c >> 4) * ESTRIDE, base_lo + (c & 15u) * ESTRIDE); };
+    auto step1 = [&](uint32_t c) { step(base_hi + (c >> 4) * NT::ROW, base_lo + (c & 15u) * NT::ROW); };
     {
         uint32_t j = 0;
-        const uint32_t head = min(n, (uint32_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(txt) & 15u)) & 15u));
-        for (; j < head; ++j) {
-            const uint32_t c = ldg1(txt + j);
-            step1(c);
+        for (; j < txt_head; ++j) step1(ldg1(txt + j));
+        while (j + 16 <= n) {
+            const uint4 cur = txt_nxt;
+            if (j + 32 <= n) txt_nxt = ldg16(txt + j + 16);
+            step4(cur.x);
+            step4(cur.y);
+            step4(cur.z);
+            step4(cur.w);
+            j += 16;
         }
-        if (j + 16 <= n) {
-            uint4 nxt = ldg16(txt + j);
-            while (j + 16 <= n) {
-                const uint4 cur = nxt;
-                if (j + 32 <= n) nxt = ldg16(txt + j + 16);
-                step4(cur.x);
-                step4(cur.y);
-                step4(cur.z);
-                step4(cur.w);
-                j += 16;
-            }
-        }
-        for (; j < n; ++j) {
-            const uint32_t c = ldg1(txt + j);
-            step1(c);
-        }
+        for (; j < n; ++j) step1(ldg1(txt + j));
     }
     uint32_t score = n;
 #pragma unroll

@@ -20,20 +20,18 @@ template <int K>
 __global__ void __launch_bounds__(BitparConfig<K>::THREADS)
     lev_bitpar_cross_kernel(PairSpace ps, uint32_t n_queries, uint32_t cands_per_block, uint32_t chunk) {
     constexpr int T = BitparConfig<K>::THREADS;
-    constexpr uint32_t ESTRIDE = T * K * 4;
-    extern __shared__ __align__(16) unsigned char xsm[]; // [32 entries][T][K] u32 | candidate chunk (chunk + 32 B)
-    unsigned char *const tbl_hi = xsm, *const tbl_lo = xsm + 16 * ESTRIDE;
-    unsigned char *const cand_slot = xsm + 32 * ESTRIDE;
+    using NT = NibbleTables<K, T>;
+    extern __shared__ __align__(16) unsigned char xsm[]; // NibbleTables<K, T>::BYTES | candidate chunk (chunk + 32 B)
+    unsigned char *const cand_slot = xsm + NT::BYTES;
     const int tid = threadIdx.x;
     const uint32_t q = blockIdx.x * T + tid;
     const uint32_t n_c = (uint32_t)ps.n_c;
     const uint32_t c_lo = blockIdx.y * cands_per_block, c_hi = min(n_c, c_lo + cands_per_block);
+    const uint32_t opaque0 = (uint32_t)(ps.n_pairs >> 63); // run-time 0: see mad_lo in lev_bitpar.cuh
+    const uint32_t one = 1u + opaque0, two = 2u + opaque0;
+    const uint32_t base_hi = NT::base((uint32_t)__cvta_generic_to_shared(xsm), tid), base_lo = base_hi + NT::TABLE;
 
-#pragma unroll 8
-    for (int e = 0; e < 32; ++e) {
-#pragma unroll
-        for (int w = 0; w < K; ++w) *reinterpret_cast<uint32_t *>(xsm + e * ESTRIDE + word_offset<K, T>(tid, w)) = 0u;
-    }
+    zero_tables<K, T>(base_hi);
     const bool have = q < n_queries;
     uint32_t m = 0;
     const uint8_t *pat = nullptr;
@@ -44,18 +42,7 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS)
     }
     const bool fits = m <= 32u * K; // guaranteed by the host's choice of K; oversize queries are skipped, not corrupted
     const uint32_t s = 32u * K - (fits ? m : 0u);
-    if (have && fits)
-        for_each_byte_global(pat, m, [&](uint32_t i, uint32_t c) {
-            const uint32_t pos = s + i, bit = 1u << (pos & 31u), word_off = word_offset<K, T>(tid, pos >> 5);
-            *reinterpret_cast<uint32_t *>(tbl_hi + (c >> 4) * ESTRIDE + word_off) |= bit;
-            *reinterpret_cast<uint32_t *>(tbl_lo + (c & 15u) * ESTRIDE + word_off) |= bit;
-        });
-    uint32_t Pv0[K];
-#pragma unroll
-    for (int w = 0; w < K; ++w) {
-        const uint32_t lo_bit = 32u * w;
-        Pv0[w] = s >= lo_bit + 32u ? 0u : (s <= lo_bit ? 0xFFFFFFFFu : 0xFFFFFFFFu << (s - lo_bit));
-    }
+    if (have && fits) for_each_byte_global(pat, m, [&](uint32_t i, uint32_t c) { add_symbol<K, T>(base_hi, s + i, c); });
     const bool active = have && fits && m > 0;
 
     for (uint32_t c = c_lo; c < c_hi; ++c) {
@@ -63,27 +50,14 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS)
         const uint8_t *txt = ps.b_data + b0;
         const uint32_t n = (uint32_t)(b1 - b0);
         uint32_t Pv[K], Mv[K];
-#pragma unroll
-        for (int w = 0; w < K; ++w) Pv[w] = Pv0[w], Mv[w] = 0u;
-        auto step = [&](uint32_t h, uint32_t l) {
+        first_column<K>(s, Pv, Mv);
+        auto step = [&](uint32_t row_h, uint32_t row_l) {
             uint32_t hi[K], lo[K];
-            load_words<K, T>(tbl_hi + h * ESTRIDE, tid, hi);
-            load_words<K, T>(tbl_lo + l * ESTRIDE, tid, lo);
-            uint32_t hp_in = 1u, hn_in = 0u;
-#pragma unroll
-            for (int w = 0; w < K; ++w) {
-                const uint32_t eqc = w == 0 ? (hi[w] & lo[w]) : ((hi[w] & lo[w]) | hn_in);
-                const uint32_t xv = (hi[w] & lo[w]) | Mv[w];
-                const uint32_t xh = (((eqc & Pv[w]) + Pv[w]) ^ Pv[w]) | eqc;
-                const uint32_t ph = Mv[w] | ~(xh | Pv[w]);
-                const uint32_t mh = Pv[w] & xh;
-                const uint32_t phs = ph * 2u + hp_in;
-                const uint32_t mhs = mh * 2u + hn_in;
-                Pv[w] = mhs | ~(xv | phs);
-                Mv[w] = phs & xv;
-                if (w + 1 < K) hp_in = ph >> 31, hn_in = mh >> 31;
-            }
+            load_words<K, T>(row_h, hi);
+            load_words<K, T>(row_l, lo);
+            column_step<K>(hi, lo, Pv, Mv, one, two);
         };
+        auto step1 = [&](uint32_t ch) { step(base_hi + (ch >> 4) * NT::ROW, base_lo + (ch & 15u) * NT::ROW); };
         for (uint32_t c0 = 0; c0 < n; c0 += chunk) {
             const uint32_t len = min(n - c0, chunk);
             __syncthreads(); // the previous chunk / candidate has been consumed by every thread
@@ -93,22 +67,15 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS)
                 const unsigned char *cs = cand_slot + mis;
                 uint32_t j = 0;
                 const uint32_t head = min(len, (4u - (mis & 3u)) & 3u); // up to the next 4-byte boundary of the slot
-                for (; j < head; ++j) {
-                    const uint32_t ch = cs[j];
-                    step(ch >> 4, ch & 15u);
-                }
+                for (; j < head; ++j) step1(cs[j]);
                 for (; j + 4 <= len; j += 4) {
-                    const uint32_t word = *reinterpret_cast<const uint32_t *>(cs + j); // broadcast: same address in every lane
-                    const uint32_t wh = (word >> 4) & 0x0F0F0F0Fu, wl = word & 0x0F0F0F0Fu;
-                    step(wh & 0xFFu, wl & 0xFFu);
-                    step((wh >> 8) & 0xFFu, (wl >> 8) & 0xFFu);
-                    step((wh >> 16) & 0xFFu, (wl >> 16) & 0xFFu);
-                    step(wh >> 24, wl >> 24);
+                    const NibbleWord nw = split_nibbles(*reinterpret_cast<const uint32_t *>(cs + j)); // broadcast: same address in every lane
+                    step(row_of<0>(nw.hi, base_hi), row_of<0>(nw.lo, base_lo));
+                    step(row_of<1>(nw.hi, base_hi), row_of<1>(nw.lo, base_lo));
+                    step(row_of<2>(nw.hi, base_hi), row_of<2>(nw.lo, base_lo));
+                    step(row_of<3>(nw.hi, base_hi), row_of<3>(nw.lo, base_lo));
                 }
-                for (; j < len; ++j) {
-                    const uint32_t ch = cs[j];
-                    step(ch >> 4, ch & 15u);
-                }
+                for (; j < len; ++j) step1(cs[j]);
             }
         }
         uint32_t score = n; // D[m][n] = n + popc(Pv) - popc(Mv) of the final column (free rows carry delta 0)
