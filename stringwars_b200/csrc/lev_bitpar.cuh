@@ -155,16 +155,28 @@ __device__ __forceinline__ void zero_tables(uint32_t base) {
 // Xh, so Eq = HI & LO is never materialised (it only appears inside two 3-input LOP3s): 7 logic ops per word. The
 // add is ONE 32K-bit add (a carry chain, 1 op per word) instead of Myers' per-word blocks, so no word waits for the
 // deltas of the word above it and no block carry has to be folded into Eq. Shifted deltas: word 0 takes the
-// horizontal delta of DP row 0 (+1) as x * 2 + 1 / x * 2 (IMAD, FMA pipe); the words above take the bit leaving
-// the word below through one funnel shift (SHF.L.W). `one`, `two`: run-time 1 and 2 (see mad_lo).
-template <int K>
-__device__ __forceinline__ void column_step(const uint32_t (&hi)[K], const uint32_t (&lo)[K], uint32_t (&Pv)[K], uint32_t (&Mv)[K],
-                                            uint32_t one, uint32_t two) {
+// horizontal delta entering the block as x * 2 + carry (IMAD, FMA pipe); the words above take the bit leaving the
+// word below through one funnel shift (SHF.L.W). `one`, `two`: run-time 1 and 2 (see mad_lo).
+//
+// CARRY = false: the block starts at DP row 0, whose horizontal delta is always +1 (thread-per-pair kernels).
+// CARRY = true: the block sits below another one (lane-group kernel): hp_in / hn_in are the +1 / -1 horizontal delta
+// bits leaving the block above; a -1 acts as a match in the block's first row (Myers' block rule, one more LOP3).
+// ph_top / mh_top return the top word's unshifted deltas: their bit 31 is what leaves this block.
+template <int K, bool CARRY>
+__device__ __forceinline__ void column_step_io(const uint32_t (&hi)[K], const uint32_t (&lo)[K], uint32_t (&Pv)[K], uint32_t (&Mv)[K],
+                                               uint32_t one, uint32_t two, uint32_t hp_in, uint32_t hn_in, uint32_t &ph_top,
+                                               uint32_t &mh_top) {
     uint32_t t[K], x[K], sum[K];
 #pragma unroll
     for (int w = 0; w < K; ++w) {
-        t[w] = lop3<0x80>(hi[w], lo[w], Pv[w]); // Eq & Pv
-        x[w] = lop3<0xEA>(hi[w], lo[w], Mv[w]); // Eq | Mv
+        if (CARRY && w == 0) {
+            const uint32_t eqc = lop3<0xEA>(hi[w], lo[w], hn_in); // Eq | (-1 entering row 0)
+            t[w] = eqc & Pv[w];
+            x[w] = eqc | Mv[w];
+        } else {
+            t[w] = lop3<0x80>(hi[w], lo[w], Pv[w]); // Eq & Pv
+            x[w] = lop3<0xEA>(hi[w], lo[w], Mv[w]); // Eq | Mv
+        }
     }
     add_wide<K>(t, Pv, sum, one);
     uint32_t ph_below = 0u, mh_below = 0u;
@@ -173,21 +185,29 @@ __device__ __forceinline__ void column_step(const uint32_t (&hi)[K], const uint3
         const uint32_t d0 = lop3<0xBE>(sum[w], Pv[w], x[w]); // ((t + Pv) ^ Pv) | x
         const uint32_t ph = lop3<0xF1>(Mv[w], d0, Pv[w]);    // Mv | ~(D0 | Pv)
         const uint32_t mh = Pv[w] & d0;
-        const uint32_t phs = w == 0 ? mad_lo(ph, two, one) : __funnelshift_l(ph_below, ph, 1);
-        const uint32_t mhs = w == 0 ? mad_lo(mh, two, 0u) : __funnelshift_l(mh_below, mh, 1);
+        const uint32_t phs = w == 0 ? mad_lo(ph, two, CARRY ? hp_in : one) : __funnelshift_l(ph_below, ph, 1);
+        const uint32_t mhs = w == 0 ? mad_lo(mh, two, CARRY ? hn_in : 0u) : __funnelshift_l(mh_below, mh, 1);
         ph_below = ph, mh_below = mh;
         Pv[w] = lop3<0xF1>(mhs, d0, phs); // Mh' | ~(D0 | Ph')
         Mv[w] = phs & d0;
     }
+    ph_top = ph_below, mh_top = mh_below;
+}
+template <int K>
+__device__ __forceinline__ void column_step(const uint32_t (&hi)[K], const uint32_t (&lo)[K], uint32_t (&Pv)[K], uint32_t (&Mv)[K],
+                                            uint32_t one, uint32_t two) {
+    uint32_t ph_top, mh_top;
+    column_step_io<K, false>(hi, lo, Pv, Mv, one, two, 0u, 0u, ph_top, mh_top);
 }
 
-// Column 0 of the DP matrix for a top-aligned pattern of m = 32K - s rows: rows below the pattern (bit < s) carry
-// vertical delta 0, pattern rows +1.
+// Column 0 of the DP matrix for a top-aligned pattern whose first symbol sits at global bit position s, for the K
+// words that start at global bit position `first`: rows below the pattern (bit < s) carry vertical delta 0, pattern
+// rows +1.
 template <int K>
-__device__ __forceinline__ void first_column(uint32_t s, uint32_t (&Pv)[K], uint32_t (&Mv)[K]) {
+__device__ __forceinline__ void first_column(uint32_t s, uint32_t (&Pv)[K], uint32_t (&Mv)[K], uint32_t first = 0u) {
 #pragma unroll
     for (int w = 0; w < K; ++w) {
-        const uint32_t lo_bit = 32u * w;
+        const uint32_t lo_bit = first + 32u * w;
         Pv[w] = s >= lo_bit + 32u ? 0u : (s <= lo_bit ? 0xFFFFFFFFu : 0xFFFFFFFFu << (s - lo_bit));
         Mv[w] = 0u;
     }

@@ -18,7 +18,7 @@
 //
 // <G,K> = <8,2> 512, <16,2> 1024, <32,2> 2048, <32,4> 4096 rows per strip. Parity: bit-exact with the CPU oracle.
 #pragma once
-#include "common.cuh"
+#include "lev_bitpar.cuh"
 
 namespace swb {
 
@@ -29,14 +29,16 @@ template <int G, int K, bool STRIPS>
 __global__ void __launch_bounds__(BPC_THREADS)
     lev_bitpar_coop_kernel(PairSpace ps, uint64_t begin, uint64_t count, uint32_t chunk_cols, uint8_t *hscratch, uint64_t scratch_stride) {
     constexpr int T = BPC_THREADS, PAIRS_PER_BLOCK = T / G;
-    constexpr uint32_t ESTRIDE = T * K * 4; // bytes between consecutive table entries
+    using NT = NibbleTables<K, T>;
     constexpr uint32_t ROWS_PER_LANE = 32u * K, CAP = ROWS_PER_LANE * G;
     constexpr uint32_t SLOT_ROWS = CAP + 32u;
-    extern __shared__ __align__(16) unsigned char smem_bytes[]; // [32 entries][T][K] u32 | per pair: rows slot, cols slot
+    extern __shared__ __align__(16) unsigned char smem_bytes[]; // NibbleTables<K, T> | per pair: rows slot, cols slot
     const uint32_t slot_cols = chunk_cols + 32u;
     const int tid = threadIdx.x, group = tid / G, lane = tid % G;
-    unsigned char *const tbl_hi = smem_bytes + tid * (K * 4), *const tbl_lo = tbl_hi + 16 * ESTRIDE;
-    unsigned char *const rows_slot = smem_bytes + 32 * ESTRIDE + (size_t)group * (SLOT_ROWS + slot_cols);
+    const uint32_t base_hi = NT::base((uint32_t)__cvta_generic_to_shared(smem_bytes), tid), base_lo = base_hi + NT::TABLE;
+    const uint32_t opaque0 = (uint32_t)(count >> 63); // run-time 0: see mad_lo in lev_bitpar.cuh
+    const uint32_t one = 1u + opaque0, two = 2u + opaque0;
+    unsigned char *const rows_slot = smem_bytes + NT::BYTES + (size_t)group * (SLOT_ROWS + slot_cols);
     unsigned char *const cols_slot = rows_slot + SLOT_ROWS;
 
     const uint64_t local = (uint64_t)blockIdx.x * PAIRS_PER_BLOCK + group;
@@ -73,11 +75,7 @@ __global__ void __launch_bounds__(BPC_THREADS)
         const uint32_t i_end = strip_live ? min(m, strip_lo + CAP - s) : i_begin; // one past the last
         __syncwarp();
         const uint32_t mis_r = strip_live ? stage_string(rows_slot, pat + i_begin, i_end - i_begin, lane, G) : 0u;
-#pragma unroll 8
-        for (int e = 0; e < 32; ++e) {
-#pragma unroll
-            for (int w = 0; w < K; ++w) *reinterpret_cast<uint32_t *>(tbl_hi + e * ESTRIDE + 4 * w) = 0u;
-        }
+        zero_tables<K, T>(base_hi);
         __syncwarp();
         const unsigned char *rows_s = rows_slot + mis_r;
         const uint32_t base = strip_lo + ROWS_PER_LANE * (uint32_t)lane; // first global bit position of this lane
@@ -86,19 +84,11 @@ __global__ void __launch_bounds__(BPC_THREADS)
         if (lane_live) {
             const uint32_t i_lo = max(i_begin, base > s ? base - s : 0u), i_hi = min(i_end, base + ROWS_PER_LANE - s);
             for (uint32_t i = i_lo; i < i_hi; ++i) {
-                const uint32_t c = rows_s[i - i_begin], q = s + i - base; // local bit position 0 .. 32K-1
-                const uint32_t bit = 1u << (q & 31u), word_off = (q >> 5) * 4u;
-                *reinterpret_cast<uint32_t *>(tbl_hi + (c >> 4) * ESTRIDE + word_off) |= bit;
-                *reinterpret_cast<uint32_t *>(tbl_lo + (c & 15u) * ESTRIDE + word_off) |= bit;
+                add_symbol<K, T>(base_hi, s + i - base, rows_s[i - i_begin]); // local bit position 0 .. 32K-1
             }
         }
         uint32_t Pv[K], Mv[K];
-#pragma unroll
-        for (int w = 0; w < K; ++w) {
-            const uint32_t lo_bit = base + 32u * w; // rows below the pattern: vertical delta 0; pattern rows: +1
-            Pv[w] = s >= lo_bit + 32u ? 0u : (s <= lo_bit ? 0xFFFFFFFFu : 0xFFFFFFFFu << (s - lo_bit));
-            Mv[w] = 0u;
-        }
+        first_column<K>(s, Pv, Mv, base);
         const bool from_scratch = STRIPS && r > 0 && lane == 0;                          // delta bits come from the previous strip
         const bool to_scratch = STRIPS && strip_live && r + 1 < strips && lane == G - 1; // ... or go to the next one
         uint32_t send = 0;
@@ -119,40 +109,18 @@ __global__ void __launch_bounds__(BPC_THREADS)
                 if (jj < len_c) {
                     const uint32_t c = cols_s[jj];
                     uint32_t hi[K], lo[K];
-                    const unsigned char *ph_ = tbl_hi + (c >> 4) * ESTRIDE, *pl_ = tbl_lo + (c & 15u) * ESTRIDE;
-                    if constexpr (K == 2) {
-                        const uint2 vh = *reinterpret_cast<const uint2 *>(ph_), vl = *reinterpret_cast<const uint2 *>(pl_);
-                        hi[0] = vh.x, hi[1] = vh.y, lo[0] = vl.x, lo[1] = vl.y;
-                    } else if constexpr (K == 4) {
-                        const uint4 vh = *reinterpret_cast<const uint4 *>(ph_), vl = *reinterpret_cast<const uint4 *>(pl_);
-                        hi[0] = vh.x, hi[1] = vh.y, hi[2] = vh.z, hi[3] = vh.w, lo[0] = vl.x, lo[1] = vl.y, lo[2] = vl.z, lo[3] = vl.w;
-                    } else {
-#pragma unroll
-                        for (int w = 0; w < K; ++w) {
-                            hi[w] = *reinterpret_cast<const uint32_t *>(ph_ + 4 * w);
-                            lo[w] = *reinterpret_cast<const uint32_t *>(pl_ + 4 * w);
-                        }
-                    }
+                    load_words<K, T>(base_hi + (c >> 4) * NT::ROW, hi);
+                    load_words<K, T>(base_lo + (c & 15u) * NT::ROW, lo);
                     uint32_t in = recv;
                     if (STRIPS && from_scratch) {
                         in = next_in;
                         if (jj + 1 < len_c) next_in = hs[c0 + jj + 1];
                     }
-                    uint32_t hp_in = lane_first ? 1u : (in & 1u), hn_in = lane_first ? 0u : (in >> 1);
-#pragma unroll
-                    for (int w = 0; w < K; ++w) {
-                        const uint32_t eqc = (hi[w] & lo[w]) | hn_in;
-                        const uint32_t xv = (hi[w] & lo[w]) | Mv[w];
-                        const uint32_t xh = (((eqc & Pv[w]) + Pv[w]) ^ Pv[w]) | eqc;
-                        const uint32_t ph = Mv[w] | ~(xh | Pv[w]);
-                        const uint32_t mh = Pv[w] & xh;
-                        const uint32_t phs = ph * 2u + hp_in;
-                        const uint32_t mhs = mh * 2u + hn_in;
-                        Pv[w] = mhs | ~(xv | phs);
-                        Mv[w] = phs & xv;
-                        hp_in = ph >> 31, hn_in = mh >> 31;
-                    }
-                    send = hp_in | (hn_in << 1);
+                    const uint32_t hp_in = lane_first ? 1u : (in & 1u), hn_in = lane_first ? 0u : (in >> 1);
+                    uint32_t ph_top, mh_top;
+                    column_step_io<K, true>(hi, lo, Pv, Mv, one, two, hp_in, hn_in, ph_top, mh_top);
+                    const uint32_t hp_out = ph_top >> 31, hn_out = mh_top >> 31;
+                    send = hp_out | (hn_out << 1);
                     if (STRIPS && to_scratch) hs[c0 + jj] = (uint8_t)send;
                 }
             }
