@@ -159,7 +159,9 @@ SWB_API uint64_t swb_levenshtein_pair(swb_engine_t *engine, const uint8_t *a, si
 /* Same as swb_compute_pairs but every pointer is device memory on scope device `device_index` and the work
  * is enqueued on `cuda_stream` (a cudaStream_t; NULL = the legacy default stream) without host
  * synchronisation, except for one small internal readback when the batch needs length bucketing. Offsets
- * need not start at 0. This is what multi-process callers (one rank per GPU) and the kernel-only bench use. */
+ * need not start at 0. This is what multi-process callers (one rank per GPU) and the kernel-only bench use.
+ * Tape bytes are READ in whole aligned 16-byte pieces: up to 15 bytes before the first and after the last byte
+ * of a string may be read (never written, never used). Any cudaMalloc'ed tape satisfies this. */
 SWB_API swb_status_t swb_compute_pairs_device(swb_engine_t *engine, int device_index, const uint8_t *a_data,
                                               const uint64_t *a_offsets, const uint8_t *b_data,
                                               const uint64_t *b_offsets, size_t n_pairs, uint64_t *out,

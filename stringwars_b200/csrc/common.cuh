@@ -68,6 +68,12 @@ __device__ __forceinline__ uint4 ldg16(const void *p) { return __ldg(reinterpret
 __device__ __forceinline__ uint32_t ldg4(const void *p) { return __ldg(reinterpret_cast<const uint32_t *>(p)); }
 __device__ __forceinline__ uint32_t ldg1(const uint8_t *p) { return __ldg(p); }
 
+// Byte b (0..15, run-time) of a 16-byte piece held in registers.
+__device__ __forceinline__ uint32_t piece_byte(const uint4 &p, uint32_t b) {
+    const uint32_t w = (b & 8u) ? ((b & 4u) ? p.w : p.z) : ((b & 4u) ? p.y : p.x);
+    return (w >> (8u * (b & 3u))) & 0xFFu;
+}
+
 // Byte k (0..3, compile-time) of a 32-bit word.
 template <int KB>
 __device__ __forceinline__ uint32_t byte_of(uint32_t w) {

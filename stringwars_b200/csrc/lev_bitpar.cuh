@@ -226,13 +226,13 @@ __device__ __forceinline__ uint32_t row_of(uint32_t nibbles, uint32_t base) {
 
 // Table build for aligned 16-symbol pieces. A piece fills one 16-bit half of one table word; per symbol and table it
 // is one 16-bit read-modify-write of shared memory: IDP.4A (entry address), LDS.U16, add the position bit (each
-// position bit is set exactly once per table, so OR == ADD), STS.U16. Pieces of different words or different
+// position bit is set exactly once per table, so OR == ADD, and the add is an IMAD: FMA pipe), STS.U16. Pieces of different words or different
 // halves can never touch the same address, so NP pieces are 2*NP independent update chains: each symbol step loads
 // all 2*NP half-words first and stores them afterwards (four pieces = the whole pattern at K = 2 = eight chains,
 // 16 dependent steps instead of 64).
 // hi_base[p]: shared address of the 16-bit half piece p fills, in entry 0 of the HI table (LO is + table_bytes).
 template <int NP>
-__device__ __forceinline__ void build_pieces(const uint32_t (&hi_base)[NP], const uint4 (&piece)[NP], uint32_t table_bytes) {
+__device__ __forceinline__ void build_pieces(const uint32_t (&hi_base)[NP], const uint4 (&piece)[NP], uint32_t table_bytes, uint32_t one) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         NibbleWord nw[NP];
@@ -252,7 +252,7 @@ __device__ __forceinline__ void build_pieces(const uint32_t (&hi_base)[NP], cons
 #pragma unroll
             for (int p = 0; p < NP; ++p) vh[p] = lds16(ah[p]), vl[p] = lds16(al[p]);
 #pragma unroll
-            for (int p = 0; p < NP; ++p) sts16(ah[p], vh[p] + (1u << (4 * q + k))), sts16(al[p], vl[p] + (1u << (4 * q + k)));
+            for (int p = 0; p < NP; ++p) sts16(ah[p], mad_lo(one, 1u << (4 * q + k), vh[p])), sts16(al[p], mad_lo(one, 1u << (4 * q + k), vl[p]));
         }
     }
 }
@@ -306,7 +306,10 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
     // four pieces of words a and a+1 (64 pattern bytes). Lanes whose slots share a bank (NT::SHARERS of them per
     // warp) start at different words: lane group g works on words (2q + g) % K and +1 while group 0 works on words
     // 2q and 2q+1, so in a batch of equal lengths every access of the build is conflict-free.
-    const uint32_t pat_head = min(m, (uint32_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(pat) & 15u)) & 15u));
+    // Every byte comes out of an aligned 16-byte load: ragged heads and tails are read as the whole piece around them
+    // (never crossing into a piece that holds no string byte) and picked apart in registers.
+    const uint32_t pat_mis = (uint32_t)(reinterpret_cast<uintptr_t>(pat) & 15u);
+    const uint32_t pat_head = min(m, (16u - pat_mis) & 15u);
     const bool pieces = ((s + pat_head) & 15u) == 0u;
     const uint32_t p_begin = s + pat_head;
     constexpr uint32_t NQ = (K + 1) / 2; // quads
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
             all = all && pos >= p_begin;
         }
         if (all) {
-            build_pieces<QP>(hb, pc, NT::TABLE);
+            build_pieces<QP>(hb, pc, NT::TABLE, one);
         } else {
 #pragma unroll 1
             for (int p = 0; p < QP; ++p) {
@@ -342,25 +345,29 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
 #pragma unroll
                 for (int r = 1; r < QP; ++r)
                     if (p == r) one_pc[0] = pc[r], one_hb[0] = hb[r];
-                build_pieces<1>(one_hb, one_pc, NT::TABLE);
+                build_pieces<1>(one_hb, one_pc, NT::TABLE, one);
             }
         }
     };
     uint4 quad_a[QP], quad_b[QP];
 #pragma unroll
     for (int p = 0; p < QP; ++p) quad_a[p] = quad_b[p] = make_uint4(0, 0, 0, 0);
+    uint4 pat_first = make_uint4(0, 0, 0, 0);
+    if (pat_head) pat_first = ldg16(pat - pat_mis);
     if (pieces) load_quad(0, quad_a);
-    // Text: bytes up to the first 16-byte boundary one by one, then aligned pieces, one piece prefetched.
-    const uint32_t txt_head = min(n, (uint32_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(txt) & 15u)) & 15u));
-    uint4 txt_nxt = make_uint4(0, 0, 0, 0);
-    if (txt_head + 16u <= n) txt_nxt = ldg16(txt + txt_head);
+    // Text: the bytes up to the first 16-byte boundary, then aligned pieces, one piece prefetched.
+    const uint32_t txt_mis = (uint32_t)(reinterpret_cast<uintptr_t>(txt) & 15u);
+    const uint32_t txt_head = min(n, (16u - txt_mis) & 15u);
+    uint4 txt_first = make_uint4(0, 0, 0, 0), txt_nxt = txt_first;
+    if (txt_head) txt_first = ldg16(txt - txt_mis);
+    if (txt_head < n) txt_nxt = ldg16(txt + txt_head);
 
     zero_tables<K, T>(base_hi);
 
     // ---- build the nibble tables: bit p of HI[h] (LO[l]) is set iff the symbol at position p has high (low) nibble h (l)
     {
         uint32_t i = 0;
-        for (; i < pat_head; ++i) add_symbol<K, T>(base_hi, s + i, ldg1(pat + i));
+        for (; i < pat_head; ++i) add_symbol<K, T>(base_hi, s + i, piece_byte(pat_first, pat_mis + i));
         if (pieces) {
             // the next quad's pieces are in flight while the current quad is built (two buffers, no moves)
 #pragma unroll 1
@@ -374,16 +381,13 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
             }
             i = m;
         } else {
-            for (; i + 16 <= m; i += 16) {
+            while (i < m) { // unaligned table position: symbol by symbol out of aligned pieces
                 const uint4 piece = ldg16(pat + i);
-                const uint32_t w[4] = {piece.x, piece.y, piece.z, piece.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) add_symbol<K, T>(base_hi, s + i + 4 * q + k, (w[q] >> (8 * k)) & 0xFFu);
+                const uint32_t cnt = min(16u, m - i);
+                for (uint32_t k = 0; k < cnt; ++k) add_symbol<K, T>(base_hi, s + i + k, piece_byte(piece, k));
+                i += cnt;
             }
         }
-        for (; i < m; ++i) add_symbol<K, T>(base_hi, s + i, ldg1(pat + i));
     }
 
     // ---- column loop. No score is tracked per column: D[m][n] = D[0][n] + (sum of the vertical deltas of column n)
@@ -406,17 +410,17 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
     auto step1 = [&](uint32_t c) { step(base_hi + (c >> 4) * NT::ROW, base_lo + (c & 15u) * NT::ROW); };
     {
         uint32_t j = 0;
-        for (; j < txt_head; ++j) step1(ldg1(txt + j));
+        for (; j < txt_head; ++j) step1(piece_byte(txt_first, txt_mis + j));
         while (j + 16 <= n) {
             const uint4 cur = txt_nxt;
-            if (j + 32 <= n) txt_nxt = ldg16(txt + j + 16);
+            if (j + 16 < n) txt_nxt = ldg16(txt + j + 16); // the next piece, whole or partial
             step4(cur.x);
             step4(cur.y);
             step4(cur.z);
             step4(cur.w);
             j += 16;
         }
-        for (; j < n; ++j) step1(ldg1(txt + j));
+        for (uint32_t k = 0; j + k < n; ++k) step1(piece_byte(txt_nxt, k)); // partial last piece
     }
     uint32_t score = n;
 #pragma unroll
