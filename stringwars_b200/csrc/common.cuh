@@ -74,6 +74,43 @@ __device__ __forceinline__ uint32_t piece_byte(const uint4 &p, uint32_t b) {
     return (w >> (8u * (b & 3u))) & 0xFFu;
 }
 
+// The 16 bytes that start `mis` bytes (0..15, run-time) into the 32-byte window {lo, hi}: two rounds of word
+// selects (by 2 words, by 1 word) and four funnel shifts.
+__device__ __forceinline__ uint4 realign16(const uint4 &lo, const uint4 &hi, uint32_t mis) {
+    const bool by2 = (mis & 8u) != 0u, by1 = (mis & 4u) != 0u;
+    const uint32_t t0 = by2 ? lo.z : lo.x, t1 = by2 ? lo.w : lo.y, t2 = by2 ? hi.x : lo.z, t3 = by2 ? hi.y : lo.w, t4 = by2 ? hi.z : hi.x,
+                   t5 = by2 ? hi.w : hi.y;
+    const uint32_t u0 = by1 ? t1 : t0, u1 = by1 ? t2 : t1, u2 = by1 ? t3 : t2, u3 = by1 ? t4 : t3, u4 = by1 ? t5 : t4;
+    const uint32_t sh = (mis & 3u) * 8u;
+    return make_uint4(__funnelshift_r(u0, u1, sh), __funnelshift_r(u1, u2, sh), __funnelshift_r(u2, u3, sh), __funnelshift_r(u3, u4, sh));
+}
+
+// A string in global memory as a stream of 16-byte register pieces, whatever its alignment: piece i holds bytes
+// [16 i, 16 i + 16) of the window that starts `lead` bytes BEFORE the first string byte (lead < 16 is the caller's
+// choice of phase: 0 streams the string itself, (position of byte 0) % 16 streams pieces aligned to some other grid).
+// Only aligned 16-byte loads are issued, and only for aligned pieces that hold at least one string byte.
+struct PieceStream {
+    const uint8_t *grid; // aligned address of the aligned piece that holds window[0]
+    uint32_t mis;        // window[0] is byte `mis` of that piece
+    uint32_t lo, hi;     // the string occupies bytes [lo, hi) counted from `grid`
+    __device__ __forceinline__ void open(const uint8_t *s, uint32_t len, uint32_t lead) {
+        const uint8_t *window = s - lead;
+        mis = (uint32_t)(reinterpret_cast<uintptr_t>(window) & 15u);
+        grid = window - mis;
+        lo = mis + lead, hi = lo + len;
+    }
+    // aligned piece number a of the grid (zeros if it holds no string byte: never loaded)
+    __device__ __forceinline__ uint4 aligned(uint32_t a) const {
+        return (16u * a + 16u > lo && 16u * a < hi) ? ldg16(grid + 16u * a) : make_uint4(0, 0, 0, 0);
+    }
+    // piece i of the window out of its two aligned pieces (i and i + 1)
+    __device__ __forceinline__ uint4 combine(const uint4 &a_i, const uint4 &a_i1) const { return mis ? realign16(a_i, a_i1, mis) : a_i; }
+    __device__ __forceinline__ uint4 piece(uint32_t i) const {
+        const uint4 lo_piece = aligned(i);
+        return mis ? realign16(lo_piece, aligned(i + 1), mis) : lo_piece;
+    }
+};
+
 // Byte k (0..3, compile-time) of a 32-bit word.
 template <int KB>
 __device__ __forceinline__ uint32_t byte_of(uint32_t w) {

@@ -32,6 +32,7 @@
 // `rapidfuzz::distance::levenshtein::distance` as called at StringWars similarities/bench.rs:416-419.
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 namespace swb {
 
@@ -231,10 +232,11 @@ __device__ __forceinline__ uint32_t row_of(uint32_t nibbles, uint32_t base) {
 // all 2*NP half-words first and stores them afterwards (four pieces = the whole pattern at K = 2 = eight chains,
 // 16 dependent steps instead of 64).
 // hi_base[p]: shared address of the 16-bit half piece p fills, in entry 0 of the HI table (LO is + table_bytes).
-template <int NP>
+// ROLLED keeps the loop over the four 32-bit words of a piece as a loop (4x less code; the K >= 4 kernels are
+// instruction-cache bound otherwise: 1.5 warps per scheduler walking 70 KB of code).
+template <int NP, bool ROLLED>
 __device__ __forceinline__ void build_pieces(const uint32_t (&hi_base)[NP], const uint4 (&piece)[NP], uint32_t table_bytes, uint32_t one) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    auto word_steps = [&](auto q_static, uint32_t q) {
         NibbleWord nw[NP];
 #pragma unroll
         for (int p = 0; p < NP; ++p) nw[p] = split_nibbles(q == 0 ? piece[p].x : (q == 1 ? piece[p].y : (q == 2 ? piece[p].z : piece[p].w)));
@@ -251,9 +253,20 @@ __device__ __forceinline__ void build_pieces(const uint32_t (&hi_base)[NP], cons
             }
 #pragma unroll
             for (int p = 0; p < NP; ++p) vh[p] = lds16(ah[p]), vl[p] = lds16(al[p]);
+            // position bit 4q + k of the half: a compile-time constant when unrolled, (16^q) << k when rolled
+            const uint32_t bit = decltype(q_static)::value >= 0 ? (1u << (4 * decltype(q_static)::value + k)) : ((1u << k) << (4u * q));
 #pragma unroll
-            for (int p = 0; p < NP; ++p) sts16(ah[p], mad_lo(one, 1u << (4 * q + k), vh[p])), sts16(al[p], mad_lo(one, 1u << (4 * q + k), vl[p]));
+            for (int p = 0; p < NP; ++p) sts16(ah[p], mad_lo(one, bit, vh[p])), sts16(al[p], mad_lo(one, bit, vl[p]));
         }
+    };
+    if constexpr (ROLLED) {
+#pragma unroll 1
+        for (uint32_t q = 0; q < 4; ++q) word_steps(std::integral_constant<int, -1>{}, q);
+    } else {
+        word_steps(std::integral_constant<int, 0>{}, 0u);
+        word_steps(std::integral_constant<int, 1>{}, 1u);
+        word_steps(std::integral_constant<int, 2>{}, 2u);
+        word_steps(std::integral_constant<int, 3>{}, 3u);
     }
 }
 
@@ -300,19 +313,23 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
     const uint32_t s = 32u * K - m; // pattern symbol i lives at bit position s + i
 
     // ---- requests that can leave before the tables are zeroed
-    // Pattern: bytes up to the first 16-byte boundary one by one; from there, if the table position is 16-aligned too,
-    // aligned pieces: 16 symbols share one table word and one 16-bit half of it, and because the pattern is
-    // top-aligned every piece from position p_begin up to 32K is full. The table is built a QUAD at a time: the
-    // four pieces of words a and a+1 (64 pattern bytes). Lanes whose slots share a bank (NT::SHARERS of them per
-    // warp) start at different words: lane group g works on words (2q + g) % K and +1 while group 0 works on words
-    // 2q and 2q+1, so in a batch of equal lengths every access of the build is conflict-free.
-    // Every byte comes out of an aligned 16-byte load: ragged heads and tails are read as the whole piece around them
-    // (never crossing into a piece that holds no string byte) and picked apart in registers.
-    const uint32_t pat_mis = (uint32_t)(reinterpret_cast<uintptr_t>(pat) & 15u);
-    const uint32_t pat_head = min(m, (16u - pat_mis) & 15u);
-    const bool pieces = ((s + pat_head) & 15u) == 0u;
-    const uint32_t p_begin = s + pat_head;
+    // Pattern: streamed as 16-symbol pieces aligned to the TABLE positions (piece i = positions [16 i, 16 i + 16)),
+    // whatever the alignment of the bytes in memory (PieceStream): 16 symbols share one table word and one 16-bit
+    // half of it, and because the pattern is top-aligned every piece from position p_begin up to 32K is full; the
+    // at most 15 symbols before p_begin go in one by one. The table is built a QUAD at a time: the four pieces of
+    // words a and a+1 (64 pattern bytes). Lanes whose slots share a bank (NT::SHARERS of them per warp) start at
+    // different words: lane group g works on words (2q + g) % K and +1 while group 0 works on words 2q and 2q+1, so
+    // in a batch of equal lengths every access of the build is conflict-free.
+    PieceStream pat_stream;
+    pat_stream.open(pat, m, s & 15u);
+    const uint32_t first_piece = s >> 4;         // table piece that holds position s
+    const uint32_t p_begin = (s + 15u) & ~15u;   // first position of the first full piece
     constexpr uint32_t NQ = (K + 1) / 2; // quads
+    constexpr bool ROLLED = K >= 4;       // trade a few selects for 4x less code where the instruction cache binds
+#ifndef SWB_ROLLED_MAIN_MIN_K
+#define SWB_ROLLED_MAIN_MIN_K 4
+#endif
+    constexpr bool ROLLED_MAIN = K >= SWB_ROLLED_MAIN_MIN_K;
     constexpr int QP = K == 1 ? 2 : 4;   // pieces per quad
     const uint32_t g = NT::SHARERS == 1 ? 0u : ((uint32_t)tid / NT::TPR) % NT::SHARERS;
     // piece p of quad q: word (2q + g + p/2) % K, half p % 2
@@ -321,7 +338,7 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
 #pragma unroll
         for (int p = 0; p < QP; ++p) {
             const uint32_t pos = piece_pos(q, p);
-            if (pos >= p_begin) pc[p] = ldg16(pat + (pos - s));
+            if (pos >= p_begin) pc[p] = pat_stream.piece((pos >> 4) - first_piece);
         }
     };
     auto build_quad = [&](uint32_t q, const uint4 (&pc)[QP]) {
@@ -334,7 +351,7 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
             all = all && pos >= p_begin;
         }
         if (all) {
-            build_pieces<QP>(hb, pc, NT::TABLE, one);
+            build_pieces<QP, ROLLED>(hb, pc, NT::TABLE, one);
         } else {
 #pragma unroll 1
             for (int p = 0; p < QP; ++p) {
@@ -345,7 +362,7 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
 #pragma unroll
                 for (int r = 1; r < QP; ++r)
                     if (p == r) one_pc[0] = pc[r], one_hb[0] = hb[r];
-                build_pieces<1>(one_hb, one_pc, NT::TABLE, one);
+                build_pieces<1, true>(one_hb, one_pc, NT::TABLE, one);
             }
         }
     };
@@ -353,41 +370,26 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
 #pragma unroll
     for (int p = 0; p < QP; ++p) quad_a[p] = quad_b[p] = make_uint4(0, 0, 0, 0);
     uint4 pat_first = make_uint4(0, 0, 0, 0);
-    if (pat_head) pat_first = ldg16(pat - pat_mis);
-    if (pieces) load_quad(0, quad_a);
-    // Text: the bytes up to the first 16-byte boundary, then aligned pieces, one piece prefetched.
-    const uint32_t txt_mis = (uint32_t)(reinterpret_cast<uintptr_t>(txt) & 15u);
-    const uint32_t txt_head = min(n, (16u - txt_mis) & 15u);
-    uint4 txt_first = make_uint4(0, 0, 0, 0), txt_nxt = txt_first;
-    if (txt_head) txt_first = ldg16(txt - txt_mis);
-    if (txt_head < n) txt_nxt = ldg16(txt + txt_head);
+    if (s & 15u) pat_first = pat_stream.piece(0); // positions [16 first_piece, p_begin): its bytes s % 16 .. 15 are symbols
+    load_quad(0, quad_a);
+    // Text: streamed from its first byte, two aligned pieces ahead of the columns.
+    PieceStream txt_stream;
+    txt_stream.open(txt, n, 0u);
+    const uint32_t txt_aligned = (txt_stream.hi + 15u) >> 4; // aligned pieces that hold text bytes
+    uint4 txt_a0 = txt_stream.aligned(0), txt_a1 = txt_stream.aligned(1);
+    const uint8_t *txt_next = txt_stream.grid + 32;          // the aligned piece to request next
 
     zero_tables<K, T>(base_hi);
 
     // ---- build the nibble tables: bit p of HI[h] (LO[l]) is set iff the symbol at position p has high (low) nibble h (l)
-    {
-        uint32_t i = 0;
-        for (; i < pat_head; ++i) add_symbol<K, T>(base_hi, s + i, piece_byte(pat_first, pat_mis + i));
-        if (pieces) {
-            // the next quad's pieces are in flight while the current quad is built (two buffers, no moves)
+    for (uint32_t pos = s; pos < min(p_begin, 32u * K); ++pos) add_symbol<K, T>(base_hi, pos, piece_byte(pat_first, pos & 15u));
+    // the next quad's pieces are in flight while the current quad is built
 #pragma unroll 1
-            for (uint32_t q = 0; q < NQ; q += 2) {
-                if (q + 1 < NQ) load_quad(q + 1, quad_b);
-                build_quad(q, quad_a);
-                if (q + 1 < NQ) {
-                    if (q + 2 < NQ) load_quad(q + 2, quad_a);
-                    build_quad(q + 1, quad_b);
-                }
-            }
-            i = m;
-        } else {
-            while (i < m) { // unaligned table position: symbol by symbol out of aligned pieces
-                const uint4 piece = ldg16(pat + i);
-                const uint32_t cnt = min(16u, m - i);
-                for (uint32_t k = 0; k < cnt; ++k) add_symbol<K, T>(base_hi, s + i + k, piece_byte(piece, k));
-                i += cnt;
-            }
-        }
+    for (uint32_t q = 0; q < NQ; ++q) {
+        if (q + 1 < NQ) load_quad(q + 1, quad_b);
+        build_quad(q, quad_a);
+#pragma unroll
+        for (int p = 0; p < QP; ++p) quad_a[p] = quad_b[p];
     }
 
     // ---- column loop. No score is tracked per column: D[m][n] = D[0][n] + (sum of the vertical deltas of column n)
@@ -408,19 +410,34 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
         step(row_of<3>(nw.hi, base_hi), row_of<3>(nw.lo, base_lo));
     };
     auto step1 = [&](uint32_t c) { step(base_hi + (c >> 4) * NT::ROW, base_lo + (c & 15u) * NT::ROW); };
-    {
-        uint32_t j = 0;
-        for (; j < txt_head; ++j) step1(piece_byte(txt_first, txt_mis + j));
-        while (j + 16 <= n) {
-            const uint4 cur = txt_nxt;
-            if (j + 16 < n) txt_nxt = ldg16(txt + j + 16); // the next piece, whole or partial
+    const uint32_t full = n >> 4, rem = n & 15u;
+#pragma unroll 1
+    for (uint32_t i = 0; i < full; ++i) {
+        const uint4 cur = txt_stream.combine(txt_a0, txt_a1);
+        txt_a0 = txt_a1;
+        if (i + 2u < txt_aligned) txt_a1 = ldg16(txt_next); // whole or partial; nothing is requested past the text
+        txt_next += 16;
+        if constexpr (ROLLED_MAIN) {
+#pragma unroll 1
+            for (uint32_t w = 0; w < 4u; ++w) step4((w & 2u) ? ((w & 1u) ? cur.w : cur.z) : ((w & 1u) ? cur.y : cur.x));
+        } else {
             step4(cur.x);
             step4(cur.y);
             step4(cur.z);
             step4(cur.w);
-            j += 16;
         }
-        for (uint32_t k = 0; j + k < n; ++k) step1(piece_byte(txt_nxt, k)); // partial last piece
+    }
+    if (rem) { // the last, partial piece: whole words, then single symbols
+        const uint4 cur = txt_stream.combine(txt_a0, txt_a1);
+#pragma unroll 1
+        for (uint32_t w = 0; 4u * w < rem; ++w) {
+            uint32_t word = (w & 2u) ? ((w & 1u) ? cur.w : cur.z) : ((w & 1u) ? cur.y : cur.x);
+            if (4u * w + 4u <= rem) {
+                step4(word);
+            } else {
+                for (uint32_t k = 4u * w; k < rem; ++k, word >>= 8) step1(word & 0xFFu);
+            }
+        }
     }
     uint32_t score = n;
 #pragma unroll
