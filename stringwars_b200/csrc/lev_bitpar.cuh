@@ -232,10 +232,13 @@ __device__ __forceinline__ uint32_t row_of(uint32_t nibbles, uint32_t base) {
 // all 2*NP half-words first and stores them afterwards (four pieces = the whole pattern at K = 2 = eight chains,
 // 16 dependent steps instead of 64).
 // hi_base[p]: shared address of the 16-bit half piece p fills, in entry 0 of the HI table (LO is + table_bytes).
+// one[p]: run-time 1 for a piece that exists, 0 for one that lies below the pattern (its zero symbols then add nothing:
+// lanes with shorter patterns stay in step with their warp instead of branching).
 // ROLLED keeps the loop over the four 32-bit words of a piece as a loop (4x less code; the K >= 4 kernels are
 // instruction-cache bound otherwise: 1.5 warps per scheduler walking 70 KB of code).
 template <int NP, bool ROLLED>
-__device__ __forceinline__ void build_pieces(const uint32_t (&hi_base)[NP], const uint4 (&piece)[NP], uint32_t table_bytes, uint32_t one) {
+__device__ __forceinline__ void build_pieces(const uint32_t (&hi_base)[NP], const uint4 (&piece)[NP], uint32_t table_bytes,
+                                             const uint32_t (&one)[NP]) {
     auto word_steps = [&](auto q_static, uint32_t q) {
         NibbleWord nw[NP];
 #pragma unroll
@@ -256,7 +259,7 @@ __device__ __forceinline__ void build_pieces(const uint32_t (&hi_base)[NP], cons
             // position bit 4q + k of the half: a compile-time constant when unrolled, (16^q) << k when rolled
             const uint32_t bit = decltype(q_static)::value >= 0 ? (1u << (4 * decltype(q_static)::value + k)) : ((1u << k) << (4u * q));
 #pragma unroll
-            for (int p = 0; p < NP; ++p) sts16(ah[p], mad_lo(one, bit, vh[p])), sts16(al[p], mad_lo(one, bit, vl[p]));
+            for (int p = 0; p < NP; ++p) sts16(ah[p], mad_lo(one[p], bit, vh[p])), sts16(al[p], mad_lo(one[p], bit, vl[p]));
         }
     };
     if constexpr (ROLLED) {
@@ -342,29 +345,17 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
         }
     };
     auto build_quad = [&](uint32_t q, const uint4 (&pc)[QP]) {
-        uint32_t hb[QP];
-        bool all = true;
+        uint32_t hb[QP], exists[QP];
+        bool any = false;
 #pragma unroll
         for (int p = 0; p < QP; ++p) {
             const uint32_t pos = piece_pos(q, p);
             hb[p] = base_hi + NT::word(pos >> 5) + ((pos >> 3) & 2u);
-            all = all && pos >= p_begin;
+            exists[p] = pos >= p_begin ? one : 0u;
+            any = any || pos >= p_begin;
         }
-        if (all) {
-            build_pieces<QP, ROLLED>(hb, pc, NT::TABLE, one);
-        } else {
-#pragma unroll 1
-            for (int p = 0; p < QP; ++p) {
-                if (piece_pos(q, p) < p_begin) continue;
-                // dynamic p: select the piece and its base without indexing the register arrays
-                uint4 one_pc[1] = {pc[0]};
-                uint32_t one_hb[1] = {hb[0]};
-#pragma unroll
-                for (int r = 1; r < QP; ++r)
-                    if (p == r) one_pc[0] = pc[r], one_hb[0] = hb[r];
-                build_pieces<1, true>(one_hb, one_pc, NT::TABLE, one);
-            }
-        }
+        // skipped only if no lane of the warp has a piece in this quad (warp-uniform: no divergence in ragged batches)
+        if (__any_sync(__activemask(), any)) build_pieces<QP, ROLLED>(hb, pc, NT::TABLE, exists);
     };
     uint4 quad_a[QP], quad_b[QP];
 #pragma unroll
