@@ -3,15 +3,15 @@
 // Same recurrence and nibble tables as lev_bitpar.cuh, but the pattern's bit-vector is split over the G lanes of
 // a sub-warp group, K 32-bit words per lane (capacity CAP = 32*G*K rows per strip). A block of 32*K rows only
 // needs the horizontal delta (+1 / 0 / -1, two bits) leaving the block above it, so the lanes run as an
-// anti-diagonal wavefront over (row block, column): at step t lane l advances column t - l and hands its two
-// delta bits to lane l + 1 with one `__shfl_up_sync`. The group stages the strings into shared memory with
+// anti-diagonal wavefront over (row block, column group): at step t lane l advances the four columns of group t - l
+// and hands their delta bits to lane l + 1 with one `__shfl_up_sync`. The group stages the strings into shared memory with
 // coalesced 16-byte loads; each lane builds the table slice of its own rows.
 //
 // No length limits:
 //  * the TEXT is streamed through shared memory in chunks of `chunk_cols` bytes (the per-lane state simply
 //    carries over; each chunk costs G-1 fill/drain steps);
 //  * a PATTERN longer than CAP is processed in row strips of CAP rows; the two delta bits leaving a strip's last
-//    lane are parked per column in a global scratch row (1 byte per column) and fed to lane 0 of the next strip.
+//    lane are parked per column in a global scratch row (1 byte per four columns) and fed to lane 0 of the next strip.
 // The pattern is top-aligned over all strips (see lev_bitpar.cuh); lanes of strip 0 that hold nothing but free rows
 // stay idle (the first lane holding pattern rows takes the constant +1 delta of DP row 0). The distance is
 // n + sum of popc(Pv) - popc(Mv) over all lanes and strips after the last column: nothing is tracked per step.
@@ -93,35 +93,69 @@ __global__ void __launch_bounds__(BPC_THREADS)
         const bool to_scratch = STRIPS && strip_live && r + 1 < strips && lane == G - 1; // ... or go to the next one
         uint32_t send = 0;
 
-        // ---- the text, one shared-memory chunk at a time
+        // ---- the text, one shared-memory chunk at a time, FOUR columns per wavefront step: lane l computes columns
+        // 4(t - l) .. 4(t - l) + 3 of its row block at step t and hands the four pairs of delta bits leaving the block to
+        // lane l + 1 in one shuffle (the shuffle, the loop control and the text fetch are paid once per four columns).
+        // Delta bits travel most-significant-first in two nibbles (+1 bits in 3..0, -1 bits in 7..4) so that the
+        // producer appends a bit with one funnel shift and the consumer takes one off the top with one shift.
         for (uint32_t c0 = 0; c0 < n_max; c0 += chunk_cols) {
             const uint32_t len_c = (lane_live && c0 < n) ? min(n - c0, chunk_cols) : 0u;
             const uint32_t len_stage = (strip_live && c0 < n) ? min(n - c0, chunk_cols) : 0u;
             __syncwarp(); // every lane is done with the previous chunk
-            const uint32_t mis_c = len_stage ? stage_string(cols_slot, txt + c0, len_stage, lane, G) : 0u;
+            if (len_stage) { // text bytes c0 .. c0 + len_stage - 1 land at cols_slot[0 ..] whatever their alignment in memory
+                PieceStream ts;
+                ts.open(txt + c0, len_stage, 0u);
+                for (uint32_t p = lane; 16u * p < len_stage; p += G) *reinterpret_cast<uint4 *>(cols_slot + 16u * p) = ts.piece(p);
+            }
             __syncwarp();
-            const unsigned char *cols_s = cols_slot + mis_c;
-            uint32_t next_in = (STRIPS && from_scratch && len_c) ? hs[c0] : 0u; // prefetched delta bits of the next column
-            const uint32_t steps = min(n_max - c0, chunk_cols) + G - 1;
+            const uint32_t *cols32 = reinterpret_cast<const uint32_t *>(cols_slot);
+            const uint32_t my_groups = (len_c + 3u) >> 2;
+            const uint32_t steps = ((min(n_max - c0, chunk_cols) + 3u) >> 2) + G - 1;
+            uint8_t *const hs_c = STRIPS ? hs + (c0 >> 2) : nullptr; // one scratch byte per four columns
+            uint32_t word_next = 0u, in_next = 0u;
+            {
+                const uint32_t gg = 0u - (uint32_t)lane;
+                if (gg < my_groups) word_next = cols32[gg];
+                if (STRIPS && from_scratch && my_groups) in_next = hs_c[0];
+            }
             for (uint32_t t = 0; t < steps; ++t) {
                 const uint32_t recv = __shfl_up_sync(0xffffffffu, send, 1, G);
-                const uint32_t jj = t - (uint32_t)lane; // column inside the chunk
-                if (jj < len_c) {
-                    const uint32_t c = cols_s[jj];
-                    uint32_t hi[K], lo[K];
-                    load_words<K, T>(base_hi + (c >> 4) * NT::ROW, hi);
-                    load_words<K, T>(base_lo + (c & 15u) * NT::ROW, lo);
+                const uint32_t gg = t - (uint32_t)lane; // column group inside the chunk
+                const uint32_t word = word_next;
+                if (gg + 1u < my_groups) word_next = cols32[gg + 1u];
+                if (gg < my_groups) {
+                    const NibbleWord nw = split_nibbles(word);
+                    uint32_t hi[4][K], lo[4][K];
+                    load_words<K, T>(row_of<0>(nw.hi, base_hi), hi[0]);
+                    load_words<K, T>(row_of<0>(nw.lo, base_lo), lo[0]);
+                    load_words<K, T>(row_of<1>(nw.hi, base_hi), hi[1]);
+                    load_words<K, T>(row_of<1>(nw.lo, base_lo), lo[1]);
+                    load_words<K, T>(row_of<2>(nw.hi, base_hi), hi[2]);
+                    load_words<K, T>(row_of<2>(nw.lo, base_lo), lo[2]);
+                    load_words<K, T>(row_of<3>(nw.hi, base_hi), hi[3]);
+                    load_words<K, T>(row_of<3>(nw.lo, base_lo), lo[3]);
                     uint32_t in = recv;
                     if (STRIPS && from_scratch) {
-                        in = next_in;
-                        if (jj + 1 < len_c) next_in = hs[c0 + jj + 1];
+                        in = in_next;
+                        if (gg + 1u < my_groups) in_next = hs_c[gg + 1u];
                     }
-                    const uint32_t hp_in = lane_first ? 1u : (in & 1u), hn_in = lane_first ? 0u : (in >> 1);
-                    uint32_t ph_top, mh_top;
-                    column_step_io<K, true>(hi, lo, Pv, Mv, one, two, hp_in, hn_in, ph_top, mh_top);
-                    const uint32_t hp_out = ph_top >> 31, hn_out = mh_top >> 31;
-                    send = hp_out | (hn_out << 1);
-                    if (STRIPS && to_scratch) hs[c0 + jj] = (uint8_t)send;
+                    if (lane_first) in = 0x0Fu; // DP row 0 enters here: +1 in every column
+                    uint32_t in_p = in << 28, in_n = (in >> 4) << 28; // next column's bit on top
+                    uint32_t out_p = 0u, out_n = 0u;
+                    const uint32_t cols_here = min(4u, len_c - 4u * gg);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (k == 0 || (uint32_t)k < cols_here) {
+                            uint32_t ph_top, mh_top;
+                            column_step_io<K, true>(hi[k], lo[k], Pv, Mv, one, two, in_p >> 31, in_n >> 31, ph_top, mh_top);
+                            out_p = __funnelshift_l(ph_top, out_p, 1), out_n = __funnelshift_l(mh_top, out_n, 1);
+                        } else { // past the end of the text: keep the bit order
+                            out_p <<= 1, out_n <<= 1;
+                        }
+                        in_p = mad_lo(in_p, two, 0u), in_n = mad_lo(in_n, two, 0u);
+                    }
+                    send = out_p | (out_n << 4);
+                    if (STRIPS && to_scratch) hs_c[gg] = (uint8_t)send;
                 }
             }
         }
