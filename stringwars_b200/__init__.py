@@ -10,6 +10,6 @@ from .szs import (  # noqa: F401
     DeviceScope, LevenshteinDistances, LevenshteinDistancesUtf8, NeedlemanWunschScores, SmithWatermanScores,
     device_count, launch_count, multiprocessor_count, unary_class_costs,
 )
-from .tape import BytesTape, PinnedBuffer  # noqa: F401
+from .tape import BytesTape, PinnedBuffer, unified_mat  # noqa: F401
 
 __version__ = "0.1.0"

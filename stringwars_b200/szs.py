@@ -22,7 +22,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from .tape import BytesTape, TapeLike, as_tape
+from .tape import BytesTape, TapeLike, as_tape, unified_mat
 
 ALGO_AUTO, ALGO_WAVEFRONT, ALGO_BITPARALLEL = 0, 1, 2
 GAP_STRINGZILLA, GAP_BIO = 0, 1
@@ -156,7 +156,7 @@ class _Engine:
         """`engine.compute(&scope, &queries, &candidates) -> UnifiedMat` (bench.rs:587-589): allocates the matrix."""
         tq = as_tape(queries)
         tc = tq if candidates is None else as_tape(candidates)
-        matrix = np.zeros((len(tq), len(tc)), dtype=self.out_dtype)
+        matrix = unified_mat(len(tq), len(tc), self.out_dtype)
         self.compute_into(scope, tq, tc, matrix)
         return matrix
 

@@ -39,6 +39,28 @@ class PinnedBuffer:
             pass
 
 
+def unified_mat(rows: int, cols: int, dtype=np.uint64) -> np.ndarray:
+    """`UnifiedMat<usize>::new(rows, cols)` (bench.rs:130, 466-468): a result matrix the device can write without a
+    staging copy. Here: page-locked host memory from `swb_host_alloc`, returned as a (rows, cols) numpy array that
+    keeps its allocation alive."""
+    buf = PinnedBuffer(int(rows) * int(cols) * np.dtype(dtype).itemsize)
+    mat = buf.view(dtype).reshape(int(rows), int(cols))
+    mat[...] = 0
+    return _Owned(mat, buf)
+
+
+class _Owned(np.ndarray):
+    """ndarray view that holds a reference to the PinnedBuffer behind it."""
+
+    def __new__(cls, arr: np.ndarray, owner):
+        obj = arr.view(cls)
+        obj._owner = owner
+        return obj
+
+    def __array_finalize__(self, obj):
+        self._owner = getattr(obj, "_owner", None)
+
+
 class BytesTape:
     """`data[offsets[i]:offsets[i+1]]` is string i. Views share memory (`subview` is zero-copy)."""
 

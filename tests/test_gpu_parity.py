@@ -365,3 +365,79 @@ def test_cpp_harness_twin_runs(tmp_path):
     env["STRINGWARS_FILTER"] = "needleman"
     out = subprocess.run([os.path.join(root, "harness", "bench_similarities")], env=env, capture_output=True, text=True, timeout=300)
     assert "needleman_wunsch" in out.stdout and "levenshtein<1gpu>" not in out.stdout
+
+
+def test_every_alignment_and_length_around_piece_boundaries(scope, lev, oracle):
+    """The bit-vector kernels read strings as re-aligned 16-byte register pieces (PieceStream): every combination of
+    pattern / text alignment (mod 16) and of lengths around the piece and word boundaries, in all four K classes,
+    uniform-length batches (the conflict-free lane rotation) and ragged ones (pieces below a shorter pattern)."""
+    rng = np.random.default_rng(123)
+    alphabet = np.arange(0x20, 0x7F, dtype=np.uint8)
+    # fixed odd lengths: consecutive strings walk through every alignment
+    for la, lb in ((5, 9), (15, 16), (17, 33), (31, 31), (32, 47), (33, 64), (63, 63), (64, 65), (65, 100), (127, 129), (128, 250), (129, 131),
+                   (250, 250), (255, 256), (256, 301)):
+        n = 700
+        a = datasets._ragged(np.full(n, la), alphabet, rng, False)
+        b = datasets._ragged(np.full(n, lb), alphabet, rng, False)
+        _check_pairs(lev, scope, oracle, a, b)
+        assert "lev_bitpar<" in lev.last_kernel
+    # ragged lengths inside each class
+    for lo, hi in ((1, 32), (20, 64), (50, 128), (100, 256)):
+        n = 3000
+        a = datasets._ragged(rng.integers(lo, hi + 1, n), alphabet, rng, False)
+        b = datasets._ragged(rng.integers(lo, hi + 40, n), alphabet, rng, False)
+        _check_pairs(lev, scope, oracle, a, b)
+    # near-identical strings (long carry chains in the wide add) at awkward alignments
+    a = datasets._ragged(np.full(500, 251), alphabet, rng, False)
+    bdata = a.data.copy()
+    bdata[rng.integers(0, bdata.size, 300)] ^= 1
+    b = BytesTape.from_arrays(bdata, a.offsets.copy())
+    _check_pairs(lev, scope, oracle, a, b)
+
+
+def test_device_tapes_at_unaligned_base_pointers(scope, lev, oracle):
+    """Device-resident tapes whose first byte sits 0..15 bytes into the allocation and whose last byte ends the
+    payload: the aligned 16-byte pieces under the first and last string reach outside the tape bytes (never outside
+    the allocation), which is the read contract stated in include/stringwars_b200.h."""
+    import torch
+    rng = np.random.default_rng(5)
+    alphabet = np.arange(0x20, 0x7F, dtype=np.uint8)
+    dev = torch.device("cuda", 0)
+    for shift in (0, 1, 7, 8, 15):
+        for lo, hi in ((1, 16), (40, 64), (200, 256), (300, 600)):
+            n = 257
+            a = datasets._ragged(rng.integers(lo, hi + 1, n), alphabet, rng, False)
+            b = datasets._ragged(rng.integers(lo, hi + 1, n), alphabet, rng, False)
+            want = oracle.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, oracle.RAPIDFUZZ_CLASS, threads=4)
+            bufs = []
+            for t in (a, b):
+                raw = torch.zeros(shift + t.data.size + 16, dtype=torch.uint8, device=dev)
+                raw[shift:shift + t.data.size] = torch.from_numpy(np.array(t.data)).to(dev)
+                bufs.append((raw, raw[shift:], torch.from_numpy(np.array(t.offsets).view(np.int64)).to(dev)))
+            out = torch.zeros(n, dtype=torch.int64, device=dev)
+            lev.compute_pairs_device(bufs[0][1].data_ptr(), bufs[0][2].data_ptr(), bufs[1][1].data_ptr(), bufs[1][2].data_ptr(), n,
+                                     out.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            got = out.cpu().numpy().view(np.uint64)
+            assert np.array_equal(got, want), (shift, lo, hi, np.flatnonzero(got != want)[:5], lev.last_kernel)
+
+
+def test_unified_mat_cross_product(scope, lev, oracle):
+    """`compute` allocates the harness's UnifiedMat equivalent (page-locked matrix) and fills it like compute_into."""
+    tape = datasets.words_pairs(600)[0]
+    q, c = tape.subview(0, 300), tape.subview(300, 600)
+    m = lev.compute(scope, q, c)
+    assert m.shape == (300, 300) and m.dtype == np.uint64
+    m2 = sw.unified_mat(300, 300, np.uint64)
+    lev.compute_into(scope, q, c, m2)
+    assert np.array_equal(np.asarray(m), np.asarray(m2))
+    for i in (0, 17, 299):
+        want = oracle.levenshtein_pairs(*_row_pairs(q, c, i), oracle.RAPIDFUZZ_CLASS, threads=2)
+        assert np.array_equal(np.asarray(m)[i], want)
+
+
+def _row_pairs(q, c, i):
+    """Tapes for (q[i], c[j]) over all j, in the oracle's argument order."""
+    qi = q[i]
+    a = BytesTape.from_strings([qi] * len(c))
+    return a.data, a.offsets, c.data, c.offsets  # subview offsets are absolute into the shared data buffer
