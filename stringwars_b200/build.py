@@ -5,6 +5,7 @@ repo snapshot. Run as `python -m stringwars_b200.build [--force]`.
 """
 from __future__ import annotations
 
+import glob
 import os
 import subprocess
 import sys
@@ -14,8 +15,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libstringwars_b200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "lev_bitpar.cuh", "align_wavefront.cuh", "schedule.cuh",
-           os.path.join("..", "..", "include", "stringwars_b200.h")]
+HEADERS = sorted(os.path.basename(h) for h in glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join("..", "..", "include", "stringwars_b200.h")]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -596,7 +596,7 @@ static swb_status_t launch_bitpar_cross(swb_engine *eng, DeviceCtx &ctx, const P
                                         const char *name, cudaStream_t stream, const char **err) {
     constexpr int T = BitparConfig<K>::THREADS;
     const uint32_t chunk = 1024;
-    const size_t smem = (size_t)32 * T * K * 4 + chunk + 32;
+    const size_t smem = (size_t)32 * T * K * 4 + (((size_t)T * (CROSS_TILE + 1) * 4 + 15) & ~(size_t)15) + chunk + 32;
     SWB_CUDA(allow_smem((const void *)lev_bitpar_cross_kernel<K>, ctx.device, smem));
     const dim3 grid((n_queries + T - 1) / T, (unsigned)((ps.n_c + cands_per_block - 1) / cands_per_block));
     {
@@ -1115,18 +1115,32 @@ extern "C" swb_status_t swb_compute_cross(swb_engine_t *engine, const uint8_t *q
         const uint64_t a_lo = q_offsets[q_lo], a_hi = q_offsets[q_hi], b_lo = c_offsets[0], b_hi = c_offsets[n_candidates];
         SWB_CUDA(ctx.a_data.reserve(a_hi - a_lo + 64));
         SWB_CUDA(ctx.b_data.reserve(b_hi - b_lo + 64));
-        SWB_CUDA(ctx.out.reserve((q_hi - q_lo) * n_candidates * sizeof(uint64_t)));
+        // Results go to a device staging matrix and are copied out after the kernels. Writing a page-locked, mapped
+        // result matrix from inside the kernels (coalesced 128-byte segments) was measured at 23.5 GB/s on this pool,
+        // half the copy engine's 52 GB/s, so it stays an experiment (SWB_CROSS_ZEROCOPY=1).
+        uint64_t *mapped_out = nullptr;
+        static const bool zero_copy = getenv("SWB_CROSS_ZEROCOPY") && atoi(getenv("SWB_CROSS_ZEROCOPY")) != 0;
+        if (zero_copy) {
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+                mapped_out = (uint64_t *)attr.devicePointer;
+            else
+                (void)cudaGetLastError();
+        }
+        if (!mapped_out) SWB_CUDA(ctx.out.reserve((q_hi - q_lo) * n_candidates * sizeof(uint64_t)));
         uint8_t *d_a = (uint8_t *)ctx.a_data.ptr + (a_lo & 15u), *d_b = (uint8_t *)ctx.b_data.ptr + (b_lo & 15u);
         if (a_hi > a_lo) SWB_CUDA(cudaMemcpyAsync(d_a, q_data + a_lo, a_hi - a_lo, cudaMemcpyHostToDevice, ctx.copy_stream));
         if (b_hi > b_lo) SWB_CUDA(cudaMemcpyAsync(d_b, c_data + b_lo, b_hi - b_lo, cudaMemcpyHostToDevice, ctx.copy_stream));
         SWB_CUDA(cudaEventRecord(ctx.ev_offsets, ctx.copy_stream));
         SWB_CUDA(cudaStreamWaitEvent(ctx.compute_stream, ctx.ev_offsets, 0));
         PairSpace ps{d_a - a_lo, d_q_offs + q_lo, d_b - b_lo, d_c_offs, (q_hi - q_lo) * n_candidates, n_candidates, n_candidates, nullptr, (uint64_t *)ctx.out.ptr};
+        if (mapped_out) ps.stride = row_stride, ps.out = mapped_out + q_lo * row_stride;
         if (engine->kind == ENGINE_LEVENSHTEIN_UTF8) {
             if ((st = run_device_batch_utf8(engine, d, ps, q_hi - q_lo, n_candidates, a_hi - a_lo, b_hi - b_lo, ctx.compute_stream, err)) != SWB_OK) return st;
         } else if ((st = run_device_batch(engine, d, ps, ctx.compute_stream, err)) != SWB_OK) return st;
-        SWB_CUDA(cudaMemcpy2DAsync(out + q_lo * row_stride, row_stride * sizeof(uint64_t), ctx.out.ptr, n_candidates * sizeof(uint64_t),
-                                   n_candidates * sizeof(uint64_t), q_hi - q_lo, cudaMemcpyDeviceToHost, ctx.compute_stream));
+        if (!mapped_out)
+            SWB_CUDA(cudaMemcpy2DAsync(out + q_lo * row_stride, row_stride * sizeof(uint64_t), ctx.out.ptr, n_candidates * sizeof(uint64_t),
+                                       n_candidates * sizeof(uint64_t), q_hi - q_lo, cudaMemcpyDeviceToHost, ctx.compute_stream));
     }
     for (int d = 0; d < D; ++d) {
         SWB_CUDA(cudaSetDevice(scope->devs[d].device));

@@ -16,13 +16,20 @@
 
 namespace swb {
 
+constexpr int CROSS_TILE = 16; // candidates per result tile: 16 x u64 = one 128-byte segment per query row
+
 template <int K>
 __global__ void __launch_bounds__(BitparConfig<K>::THREADS)
     lev_bitpar_cross_kernel(PairSpace ps, uint32_t n_queries, uint32_t cands_per_block, uint32_t chunk) {
     constexpr int T = BitparConfig<K>::THREADS;
     using NT = NibbleTables<K, T>;
-    extern __shared__ __align__(16) unsigned char xsm[]; // NibbleTables<K, T>::BYTES | candidate chunk (chunk + 32 B)
-    unsigned char *const cand_slot = xsm + NT::BYTES;
+    extern __shared__ __align__(16) unsigned char xsm[]; // NibbleTables<K, T>::BYTES | result tile | candidate chunk (chunk + 32 B)
+    // Results leave the block as whole 128-byte row segments: a thread parks the scores of CROSS_TILE consecutive
+    // candidates in a shared tile, then the block writes 16 consecutive u64 per query row (a thread's own stores
+    // would be one 8-byte piece per row of the matrix).
+    constexpr uint32_t TILE_PITCH = CROSS_TILE + 1; // odd pitch: a warp's 32 parked scores fall into 32 banks
+    uint32_t *const tile = reinterpret_cast<uint32_t *>(xsm + NT::BYTES); // [T][TILE_PITCH] scores
+    unsigned char *const cand_slot = xsm + NT::BYTES + ((T * TILE_PITCH * 4 + 15) & ~15);
     const int tid = threadIdx.x;
     const uint32_t q = blockIdx.x * T + tid;
     const uint32_t n_c = (uint32_t)ps.n_c;
@@ -81,7 +88,23 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS)
         uint32_t score = n; // D[m][n] = n + popc(Pv) - popc(Mv) of the final column (free rows carry delta 0)
 #pragma unroll
         for (int w = 0; w < K; ++w) score += __popc(Pv[w]) - __popc(Mv[w]);
-        if (have && fits) ps.out[(uint64_t)q * ps.stride + c] = m == 0 ? n : score;
+        // park the score; flush the tile every CROSS_TILE candidates and after the last one
+        const uint32_t slot = (c - c_lo) % CROSS_TILE;
+        tile[tid * TILE_PITCH + slot] = (have && fits) ? (m == 0 ? n : score) : 0xFFFFFFFFu; // 0xFFFFFFFF: no result for this row
+        if (slot == CROSS_TILE - 1 || c + 1 == c_hi) {
+            __syncthreads();
+            const uint32_t c_first = c - slot, width = slot + 1;
+            const uint32_t q_block = blockIdx.x * T;
+            // lane -> (row, column): 16 lanes cover one row's segment, a warp covers two rows per turn
+            for (uint32_t e = tid; e < (uint32_t)T * CROSS_TILE; e += T) {
+                const uint32_t row = e / CROSS_TILE, col = e % CROSS_TILE;
+                const uint32_t qq = q_block + row;
+                const uint32_t v = tile[row * TILE_PITCH + col];
+                // rows of queries that do not fit this kernel's K are left untouched (the host never sends them here)
+                if (col < width && qq < n_queries && v != 0xFFFFFFFFu) ps.out[(uint64_t)qq * ps.stride + c_first + col] = v;
+            }
+            __syncthreads();
+        }
     }
 }
 
