@@ -25,6 +25,8 @@ extern "C" {
                          c_offsets: *const u64, n_c: usize, out: *mut u64, row_stride: usize, err: *mut *const c_char) -> c_int;
     fn swb_levenshtein_pair(engine: *mut RawEngine, a: *const u8, la: usize, b: *const u8, lb: usize, err: *mut *const c_char) -> u64;
     fn swb_multiprocessor_count(device: c_int, out: *mut c_int, err: *mut *const c_char) -> c_int;
+    fn swb_host_alloc(bytes: usize, out: *mut *mut c_void, err: *mut *const c_char) -> c_int;
+    fn swb_host_free(ptr: *mut c_void);
 }
 
 #[derive(Debug)]
@@ -103,6 +105,24 @@ impl NeedlemanWunschScores {
     }
 }
 impl Drop for NeedlemanWunschScores { fn drop(&mut self) { unsafe { swb_engine_destroy(self.0) } } }
+
+/// Row-major result matrix in page-locked host memory (`swb_host_alloc`): the stand-in for `UnifiedMat<usize>`
+/// (bench.rs:130, 466-468). The engine's result copy into it is a DMA at full PCIe rate; a `Vec<u64>` works too,
+/// at about a third of that.
+pub struct UnifiedMat { ptr: *mut u64, rows: usize, cols: usize }
+impl UnifiedMat {
+    pub fn new(rows: usize, cols: usize) -> Result<Self, Error> {
+        let (mut p, mut err) = (std::ptr::null_mut(), std::ptr::null());
+        check(unsafe { swb_host_alloc(rows * cols * 8, &mut p, &mut err) }, err)?;
+        unsafe { std::ptr::write_bytes(p as *mut u8, 0, rows * cols * 8) };
+        Ok(Self { ptr: p as *mut u64, rows, cols })
+    }
+    pub fn rows(&self) -> usize { self.rows }
+    pub fn cols(&self) -> usize { self.cols }
+    pub fn as_slice(&self) -> &[u64] { unsafe { std::slice::from_raw_parts(self.ptr, self.rows * self.cols) } }
+    pub fn as_mut_slice(&mut self) -> &mut [u64] { unsafe { std::slice::from_raw_parts_mut(self.ptr, self.rows * self.cols) } }
+}
+impl Drop for UnifiedMat { fn drop(&mut self) { unsafe { swb_host_free(self.ptr as *mut c_void) } } }
 
 /// `gpu_multiprocessor_count(device)` (utils.rs:826-836).
 pub fn multiprocessor_count(device: usize) -> Option<usize> {
