@@ -594,7 +594,7 @@ static swb_status_t launch_wavefront(swb_engine *eng, DeviceCtx &ctx, int dev_in
 template <int K>
 static swb_status_t launch_bitpar_cross(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint32_t n_queries, uint32_t cands_per_block,
                                         const char *name, cudaStream_t stream, const char **err) {
-    constexpr int T = BitparConfig<K>::THREADS;
+    constexpr int T = CrossConfig<K>::THREADS;
     const uint32_t chunk = 1024;
     const size_t smem = (size_t)32 * T * K * 4 + (((size_t)T * (CROSS_TILE + 1) * 4 + 15) & ~(size_t)15) + chunk + 32;
     SWB_CUDA(allow_smem((const void *)lev_bitpar_cross_kernel<K>, ctx.device, smem));

@@ -91,9 +91,15 @@ __device__ __forceinline__ void add_wide(const uint32_t (&a)[K], const uint32_t 
     }
 }
 
+#ifndef SWB_BITPAR_THREADS_SMALL
+#define SWB_BITPAR_THREADS_SMALL 64 // threads per block for K <= 4: measured 64 > 128 > 256 (+2 % / -2 %) at 64x64: finer blocks mix the phases
+#endif
+#ifndef SWB_BITPAR_THREADS_K8
+#define SWB_BITPAR_THREADS_K8 64
+#endif
 template <int K>
 struct BitparConfig {
-    static constexpr int THREADS = K <= 4 ? 128 : 64; // 128 * K bytes of tables per thread
+    static constexpr int THREADS = K <= 4 ? SWB_BITPAR_THREADS_SMALL : SWB_BITPAR_THREADS_K8; // 128 * K bytes of tables per thread; K = 8: 32 = 64 > 128
 };
 
 // Shared-memory layout of the nibble tables of a block of T threads with K words each.
@@ -301,7 +307,13 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
     const uint32_t one = 1u + opaque0, two = 2u + opaque0;
     const uint32_t base_hi = NT::base((uint32_t)__cvta_generic_to_shared(tbl_bytes), tid), base_lo = base_hi + NT::TABLE;
 
+#ifdef SWB_BITPAR_ZERO_FIRST
+    const PairRequest pr = pair_request(ps, begin + local); // offsets in flight while the tables are zeroed
+    zero_tables<K, T>(base_hi);
+    const PairView pv = pair_resolve(ps, pr);
+#else
     const PairView pv = pair_at(ps, begin + local);
+#endif
     // pattern = shorter string (distance is symmetric), text = longer one
     const bool swap = pv.la > pv.lb;
     const uint8_t *pat = swap ? pv.b : pv.a;
@@ -370,7 +382,9 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
     uint4 txt_a0 = txt_stream.aligned(0), txt_a1 = txt_stream.aligned(1);
     const uint8_t *txt_next = txt_stream.grid + 32;          // the aligned piece to request next
 
+#ifndef SWB_BITPAR_ZERO_FIRST
     zero_tables<K, T>(base_hi);
+#endif
 
     // ---- build the nibble tables: bit p of HI[h] (LO[l]) is set iff the symbol at position p has high (low) nibble h (l)
     for (uint32_t pos = s; pos < min(p_begin, 32u * K); ++pos) add_symbol<K, T>(base_hi, pos, piece_byte(pat_first, pos & 15u));

@@ -16,12 +16,18 @@
 
 namespace swb {
 
+// Threads (= queries) per block: a candidate is staged once per block, so wider blocks than the pair kernel's.
+template <int K>
+struct CrossConfig {
+    static constexpr int THREADS = K <= 4 ? 128 : 64;
+};
+
 constexpr int CROSS_TILE = 16; // candidates per result tile: 16 x u64 = one 128-byte segment per query row
 
 template <int K>
-__global__ void __launch_bounds__(BitparConfig<K>::THREADS)
+__global__ void __launch_bounds__(CrossConfig<K>::THREADS)
     lev_bitpar_cross_kernel(PairSpace ps, uint32_t n_queries, uint32_t cands_per_block, uint32_t chunk) {
-    constexpr int T = BitparConfig<K>::THREADS;
+    constexpr int T = CrossConfig<K>::THREADS;
     using NT = NibbleTables<K, T>;
     extern __shared__ __align__(16) unsigned char xsm[]; // NibbleTables<K, T>::BYTES | result tile | candidate chunk (chunk + 32 B)
     // Results leave the block as whole 128-byte row segments: a thread parks the scores of CROSS_TILE consecutive
