@@ -1,0 +1,270 @@
+"""CPU models of the bit tricks the CUDA kernels rely on (stringwars_b200/csrc/lev_bitpar*.cuh, common.cuh), checked
+against the oracle: the column recurrence, the delta-bit hand-over between lanes, the register re-alignment of string
+pieces and the shared-memory layout's bank behaviour. They pin the ALGEBRA on the CPU box; the kernels themselves are
+checked bit-exact on the GPU by tests/test_gpu_parity.py."""
+import itertools
+import random
+
+import numpy as np
+import pytest
+
+from oracle import pyref
+
+M32 = 0xFFFFFFFF
+
+
+def _eq_masks(pat, K):
+    """Top-aligned pattern: symbol i at bit s + i, s = 32K - m (lev_bitpar.cuh)."""
+    s = 32 * K - len(pat)
+    eq = {}
+    for i, c in enumerate(pat):
+        p = s + i
+        eq.setdefault(c, [0] * K)[p >> 5] |= 1 << (p & 31)
+    return s, eq
+
+
+def _first_column(s, K, first=0):
+    Pv = []
+    for w in range(K):
+        lo = first + 32 * w
+        Pv.append(0 if s >= lo + 32 else (M32 if s <= lo else (M32 << (s - lo)) & M32))
+    return Pv, [0] * K
+
+
+def column_step(eq, Pv, Mv, hp_in=1, hn_in=0, carry=False):
+    """column_step_io: Hyyro's single-mask form over K words, ONE wide add, IMAD shift in word 0, funnel shifts above."""
+    K = len(Pv)
+    t, x = [], []
+    for w in range(K):
+        e = eq[w] | (hn_in if (carry and w == 0) else 0)
+        t.append(e & Pv[w])
+        x.append(e | Mv[w])
+    total = sum(v << (32 * w) for w, v in enumerate(t)) + sum(v << (32 * w) for w, v in enumerate(Pv))
+    ssum = [(total >> (32 * w)) & M32 for w in range(K)]
+    ph_below = mh_below = 0
+    for w in range(K):
+        d0 = ((ssum[w] ^ Pv[w]) | x[w]) & M32
+        ph = (Mv[w] | ~(d0 | Pv[w])) & M32
+        mh = Pv[w] & d0
+        if w == 0:
+            phs, mhs = (ph * 2 + hp_in) & M32, (mh * 2 + (hn_in if carry else 0)) & M32
+        else:
+            phs, mhs = ((ph << 1) | (ph_below >> 31)) & M32, ((mh << 1) | (mh_below >> 31)) & M32
+        ph_below, mh_below = ph, mh
+        Pv[w] = (mhs | ~(d0 | phs)) & M32
+        Mv[w] = phs & d0
+    return ph_below, mh_below  # the top word's unshifted deltas: bit 31 leaves the block
+
+
+def bitpar_distance(a, b, K):
+    pat, txt = (a, b) if len(a) <= len(b) else (b, a)
+    if not pat:
+        return len(txt)
+    s, eq = _eq_masks(pat, K)
+    Pv, Mv = _first_column(s, K)
+    for c in txt:
+        column_step(eq.get(c, [0] * K), Pv, Mv)
+    return len(txt) + sum(bin(v).count("1") for v in Pv) - sum(bin(v).count("1") for v in Mv)
+
+
+def _rand_pair(rng, lo, hi, alphabet):
+    a = bytes(rng.randrange(alphabet) for _ in range(rng.randint(lo, hi)))
+    if rng.random() < 0.4:  # similar strings: long carry chains in the add
+        b = bytearray(a)
+        for _ in range(rng.randint(0, 4)):
+            if b:
+                b[rng.randrange(len(b))] = rng.randrange(alphabet)
+        b = bytes(b) + bytes(rng.randrange(alphabet) for _ in range(rng.randint(0, 9)))
+    else:
+        b = bytes(rng.randrange(alphabet) for _ in range(rng.randint(lo, hi + 20)))
+    return a, b
+
+
+@pytest.mark.parametrize("K", [1, 2, 4, 8])
+def test_column_step_matches_the_definition(K):
+    rng = random.Random(K)
+    for _ in range(150):
+        a, b = _rand_pair(rng, 0, 32 * K, rng.choice([2, 4, 26]))
+        if min(len(a), len(b)) > 32 * K:
+            continue
+        assert bitpar_distance(a, b, K) == pyref.levenshtein(a, b), (a, b)
+
+
+def coop_distance(a, b, G, K):
+    """lev_bitpar_coop.cuh: the column split over G lanes of K words, FOUR columns per wavefront step, the delta bits of
+    a step packed most-significant-first into two nibbles (+1 bits in 3..0, -1 bits in 7..4)."""
+    pat, txt = (a, b) if len(a) <= len(b) else (b, a)
+    m, n = len(pat), len(txt)
+    if m == 0:
+        return n
+    cap = 32 * G * K
+    assert m <= cap
+    s = cap - m
+    lanes = []
+    for lane in range(G):
+        base = 32 * K * lane
+        eq = {}
+        for i, c in enumerate(pat):
+            p = s + i - base
+            if 0 <= p < 32 * K:
+                eq.setdefault(c, [0] * K)[p >> 5] |= 1 << (p & 31)
+        Pv, Mv = _first_column(s, K, base)
+        lanes.append({"eq": eq, "Pv": Pv, "Mv": Mv, "live": base + 32 * K > s, "first": base <= s})
+    groups = (n + 3) // 4
+    send = [0] * G
+    for t in range(groups + G - 1):
+        recv = [0] + send[:-1]  # __shfl_up_sync(send, 1)
+        new_send = list(send)
+        for lane, L in enumerate(lanes):
+            gg = t - lane
+            if not L["live"] or not (0 <= gg < groups):
+                continue
+            inp = 0x0F if L["first"] else recv[lane]
+            in_p, in_n = (inp << 28) & M32, ((inp >> 4) << 28) & M32
+            out_p = out_n = 0
+            for k in range(4):
+                j = 4 * gg + k
+                if j < n:
+                    ph_top, mh_top = column_step(L["eq"].get(txt[j], [0] * K), L["Pv"], L["Mv"], in_p >> 31, in_n >> 31, carry=True)
+                    out_p, out_n = ((out_p << 1) | (ph_top >> 31)) & M32, ((out_n << 1) | (mh_top >> 31)) & M32
+                else:
+                    out_p, out_n = (out_p << 1) & M32, (out_n << 1) & M32
+                in_p, in_n = (in_p << 1) & M32, (in_n << 1) & M32
+            new_send[lane] = (out_p | (out_n << 4)) & M32
+        send = new_send
+    delta = sum(bin(v).count("1") for L in lanes if L["live"] for v in L["Pv"]) - sum(
+        bin(v).count("1") for L in lanes if L["live"] for v in L["Mv"])
+    return n + delta
+
+
+@pytest.mark.parametrize("G,K", [(4, 1), (8, 2), (4, 4)])
+def test_lane_group_wavefront_with_four_column_steps(G, K):
+    rng = random.Random(G * 10 + K)
+    for _ in range(40):
+        a, b = _rand_pair(rng, 1, 32 * G * K, rng.choice([2, 4, 26]))
+        if min(len(a), len(b)) > 32 * G * K:
+            continue
+        assert coop_distance(a, b, G, K) == pyref.levenshtein(a, b), (a, b)
+
+
+# ---- register re-alignment of 16-byte pieces (common.cuh: realign16, PieceStream)
+
+def realign16(lo, hi, mis):
+    """Two rounds of word selects (by 2 words, by 1 word) and four funnel shifts, on lists of four u32."""
+    w = list(lo) + list(hi)
+    by2, by1 = bool(mis & 8), bool(mis & 4)
+    t = [w[i + 2] if by2 else w[i] for i in range(6)]
+    u = [t[i + 1] if by1 else t[i] for i in range(5)]
+    sh = (mis & 3) * 8
+    return [(((u[i + 1] << 32) | u[i]) >> sh) & M32 for i in range(4)]
+
+
+def _words(b16):
+    return [int.from_bytes(b16[4 * i:4 * i + 4], "little") for i in range(4)]
+
+
+def test_realign16_is_a_byte_shift_of_the_window():
+    rng = np.random.default_rng(0)
+    window = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+    for mis in range(16):
+        got = realign16(_words(window[:16]), _words(window[16:]), mis)
+        assert got == _words(window[mis:mis + 16]), mis
+
+
+def piece_stream(mem, start, length, lead):
+    """PieceStream: yields (piece bytes, set of aligned piece numbers it loaded). `mem` is the whole address space; only
+    aligned 16-byte pieces that hold at least one string byte may be read."""
+    window = start - lead
+    mis = window % 16
+    grid = window - mis
+    lo, hi = mis + lead, mis + lead + length
+
+    def aligned(a):
+        ok = 16 * a + 16 > lo and 16 * a < hi
+        return (mem[grid + 16 * a: grid + 16 * a + 16] if ok else bytes(16)), ok
+
+    i = 0
+    while 16 * i < lead + length:
+        p0, ok0 = aligned(i)
+        loaded = {i} if ok0 else set()
+        if mis:
+            p1, ok1 = aligned(i + 1)
+            loaded |= {i + 1} if ok1 else set()
+            words = realign16(_words(p0), _words(p1), mis)
+            piece = b"".join(x.to_bytes(4, "little") for x in words)
+        else:
+            piece = p0
+        yield piece, {grid + 16 * a for a in loaded}
+        i += 1
+
+
+def test_piece_stream_reads_only_pieces_that_hold_string_bytes():
+    rng = np.random.default_rng(1)
+    mem = rng.integers(1, 256, 4096, dtype=np.uint8).tobytes()
+    for start, length, lead in itertools.product((256, 257, 263, 271, 300), (1, 5, 16, 17, 40, 100), (0, 3, 11, 15)):
+        out = bytearray()
+        for piece, touched in piece_stream(mem, start, length, lead):
+            out += piece
+            for addr in touched:
+                assert addr % 16 == 0 and addr + 16 > start and addr < start + length, (start, length, lead, addr)
+        # window byte `lead + i` is string byte i, whatever the alignment
+        assert bytes(out[lead:lead + length]) == mem[start:start + length], (start, length, lead)
+
+
+# ---- shared-memory layout of the nibble tables (lev_bitpar.cuh: NibbleTables)
+
+def _layout(K, T):
+    parts = 1 if K <= 4 else K // 4
+    sb = min(K, 4) * 4
+    tpr = 128 // sb
+    return parts, sb, tpr
+
+
+def _base(K, T, tid):
+    parts, sb, tpr = _layout(K, T)
+    return (tid // tpr) * (parts * 2 * 2048) + (tid % tpr) * sb
+
+
+@pytest.mark.parametrize("K,T", [(1, 64), (2, 64), (4, 64), (8, 64), (2, 128)])
+def test_table_layout_is_a_partition_and_lookups_are_conflict_free(K, T):
+    parts, sb, tpr = _layout(K, T)
+    seen = set()
+    for tid in range(T):
+        for part in range(parts):
+            for table in range(2):
+                for entry in range(16):
+                    a = _base(K, T, tid) + part * 4096 + table * 2048 + entry * 128
+                    cells = set(range(a, a + sb))
+                    assert not (cells & seen)
+                    seen |= cells
+    assert seen == set(range(T * K * 4 * 32))  # exactly NibbleTables::BYTES, no holes
+    # a warp's lookup (every lane its own entry) is split by the hardware into wavefronts of 128 bytes worth of lanes:
+    # within one wavefront the lanes' slots must fall into distinct banks whatever entries they ask for
+    rng = random.Random(K)
+    lanes_per_wavefront = 128 // sb
+    for warp in range(T // 32):
+        for _ in range(20):
+            entries = [rng.randrange(16) for _ in range(32)]
+            for wf in range(32 // lanes_per_wavefront):
+                banks = []
+                for lane in range(wf * lanes_per_wavefront, (wf + 1) * lanes_per_wavefront):
+                    a = _base(K, T, warp * 32 + lane) + entries[lane] * 128
+                    banks += [((a + 4 * i) // 4) % 32 for i in range(sb // 4)]
+                assert len(set(banks)) == len(banks)
+
+
+@pytest.mark.parametrize("K,T", [(2, 64), (4, 64), (8, 64)])
+def test_build_rotation_keeps_a_uniform_batch_conflict_free(K, T):
+    """Lanes whose slots share a bank start the build at different words: lane group g works on word (2q + g + p/2) % K."""
+    parts, sb, tpr = _layout(K, T)
+    sharers = 32 // tpr
+    rng = random.Random(K)
+    for q in range((K + 1) // 2):
+        for p in range(4):
+            banks = []
+            for lane in range(32):
+                g = (lane // tpr) % sharers
+                word = (2 * q + g + p // 2) % K
+                a = _base(K, T, lane) + (word >> 2) * 4096 + (word & 3) * 4 + rng.randrange(16) * 128
+                banks.append((a // 4) % 32)
+            assert len(set(banks)) == 32, (q, p)
