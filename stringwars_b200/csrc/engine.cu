@@ -22,6 +22,7 @@
 
 #include "align_wavefront.cuh"
 #include "align_wavefront_packed.cuh"
+#include "align_wavefront_packed_general.cuh"
 #include "lev_bitpar.cuh"
 #include "lev_bitpar_coop.cuh"
 #include "lev_bitpar_cross.cuh"
@@ -509,6 +510,27 @@ static swb_status_t launch_wavefront_packed(swb_engine *eng, DeviceCtx &ctx, int
     return SWB_OK;
 }
 
+template <int G, int R, bool LOCAL, bool AFFINE>
+static swb_status_t launch_wavefront_packed_general(swb_engine *eng, DeviceCtx &ctx, int dev_index, const PairSpace &ps, uint64_t begin,
+                                                    uint64_t count, const AlignCosts &cs, uint32_t max_m, uint32_t max_n, cudaStream_t stream,
+                                                    const char **err) {
+    constexpr int GPB = WF_THREADS / G;
+    const uint32_t slot_rows = round16(max_m + 16u) + 16u, slot_cols = round16(max_n + 16u) + 16u;
+    const uint32_t bound_cap = max_n + 1u;
+    const size_t smem = 2304 + (size_t)GPB * (2u * slot_rows + 2u * slot_cols + round16(bound_cap * 4u) * (AFFINE ? 2u : 1u));
+    if (smem > (size_t)ctx.max_smem_optin) return fail(err, SWB_TOO_LONG, "packed wavefront: %zu B of shared memory per block", smem);
+    SWB_CUDA(allow_smem((const void *)align_wavefront_packed_general_kernel<G, R, LOCAL, AFFINE>, ctx.device, smem));
+    const uint64_t blocks = ((count + 1) / 2 + GPB - 1) / GPB;
+    {
+        ProfileBracket bracket(eng, ctx.device, stream);
+        align_wavefront_packed_general_kernel<G, R, LOCAL, AFFINE><<<(unsigned)blocks, WF_THREADS, smem, stream>>>(
+            ps, begin, count, cs, eng->d_tables[dev_index], slot_rows, slot_cols, bound_cap);
+    }
+    g_launches++;
+    SWB_CUDA(cudaGetLastError());
+    return SWB_OK;
+}
+
 template <int G, int R>
 static swb_status_t launch_wavefront_gr(swb_engine *eng, DeviceCtx &ctx, int dev_index, const PairSpace &ps, uint64_t begin,
                                         uint64_t count, const AlignCosts &cs, bool local, bool affine, bool unary, bool narrow,
@@ -570,6 +592,30 @@ static swb_status_t launch_wavefront(swb_engine *eng, DeviceCtx &ctx, int dev_in
         SWB_PK(16, "align_wavefront_packed<G=16,R=16>")
         SWB_PK(32, "align_wavefront_packed<G=32,R=16>")
 #undef SWB_PK
+        if (pst != SWB_TOO_LONG) return pst;
+    }
+    // Packed s16x2 variant for affine gaps and / or local alignment (align_wavefront_packed_general.cuh): unary costs with
+    // mismatch <= 0 <= match, gaps <= 0, every pair of the same shape, every reachable score inside int16 with room
+    // for the gap tracks' floor: H >= 3*first + (m+n)*min(next, mismatch), H <= min(m,n)*match.
+    if (!packed_off && same_shape && (local || affine) && eng->unary && ps.len_shift == 0 && count >= 2 && cs.mismatch <= 0 && cs.match >= 0 &&
+        cs.first <= 0 && cs.next <= 0 &&
+        3 * (int64_t)cs.first + (int64_t)(max_m + max_n) * std::min(cs.next, cs.mismatch) > -28000 &&
+        (int64_t)std::min(max_m, max_n) * cs.match < 32000) {
+        swb_status_t pst = SWB_TOO_LONG;
+#define SWB_PG(G, NAME)                                                                                                                        \
+        if (pst == SWB_TOO_LONG && (max_m <= (uint32_t)(G) * 16u || (G) == 32)) {                                                                \
+            eng->last_kernel = NAME;                                                                                                           \
+            if (local && affine) pst = launch_wavefront_packed_general<G, 16, true, true>(eng, ctx, dev_index, ps, begin, count, cs, max_m, max_n, stream, err);        \
+            else if (local) pst = launch_wavefront_packed_general<G, 16, true, false>(eng, ctx, dev_index, ps, begin, count, cs, max_m, max_n, stream, err);            \
+            else pst = launch_wavefront_packed_general<G, 16, false, true>(eng, ctx, dev_index, ps, begin, count, cs, max_m, max_n, stream, err);                        \
+        }
+        SWB_PG(1, "align_wavefront_packed_general<G=1,R=16>")
+        SWB_PG(2, "align_wavefront_packed_general<G=2,R=16>")
+        SWB_PG(4, "align_wavefront_packed_general<G=4,R=16>")
+        SWB_PG(8, "align_wavefront_packed_general<G=8,R=16>")
+        SWB_PG(16, "align_wavefront_packed_general<G=16,R=16>")
+        SWB_PG(32, "align_wavefront_packed_general<G=32,R=16>")
+#undef SWB_PG
         if (pst != SWB_TOO_LONG) return pst;
     }
     // Narrowest group that covers the pattern in one strip; if the class's longest text makes the block's staged

@@ -166,7 +166,11 @@ def test_alignment_scores(scope, oracle, open_, extend, conv, local):
     btc, costs = sw.unary_class_costs(2, -1)
     cls = sw.SmithWatermanScores if local else sw.NeedlemanWunschScores
     engine = cls(scope, btc, costs, open_, extend).set_gap_convention(conv)
-    for a, b in (datasets.acgt_pairs(300, 100, seed=2), datasets.words_pairs(600, seed=2), datasets.acgt_pairs(40, 1024, seed=3)):
+    # same-shape batches take the packed s16x2 kernels (an odd count, lopsided shapes, two row strips at 1024, single pair)
+    lopsided = (datasets.acgt_pairs(301, 100, seed=5)[0], datasets.acgt_pairs(301, 257, seed=6)[1])
+    tall = (datasets.acgt_pairs(33, 700, seed=7)[0], datasets.acgt_pairs(33, 40, seed=8)[1])
+    for a, b in (datasets.acgt_pairs(300, 100, seed=2), datasets.words_pairs(600, seed=2), datasets.acgt_pairs(40, 1024, seed=3), lopsided, tall,
+                 datasets.acgt_pairs(1, 64, seed=9)):
         got = engine.compute_pairs(scope, a, b)
         want = oracle.align_pairs(a.data, a.offsets, b.data, b.offsets, btc, costs, open_, extend, conv, local, threads=8)
         bad = np.flatnonzero(got != want)
