@@ -268,3 +268,109 @@ def test_build_rotation_keeps_a_uniform_batch_conflict_free(K, T):
                 a = _base(K, T, lane) + (word >> 2) * 4096 + (word & 3) * 4 + rng.randrange(16) * 128
                 banks.append((a // 4) % 32)
             assert len(set(banks)) == 32, (q, p)
+
+
+# ---- packed s16x2 arithmetic of the affine / local wavefront (align_wavefront_packed_general.cuh)
+
+def _s16(v):
+    v &= 0xFFFF
+    return v - 0x10000 if v & 0x8000 else v
+
+
+def _halves(p):
+    return _s16(p), _s16(p >> 16)
+
+
+def _pack(lo, hi):
+    return ((hi & 0xFFFF) << 16) | (lo & 0xFFFF)
+
+
+def pk_both(v):
+    return ((v & 0xFFFF) * 0x00010001) & M32
+
+
+def viaddmax_s16x2(a, b, c):
+    """VIADDMNMX.S16x2: per half max(a + b, c) with wrapping 16-bit adds (what the kernel relies on NOT happening)."""
+    out = []
+    for x, y, z in zip(_halves(a), _halves(b), _halves(c)):
+        out.append(max(_s16(x + y), z))
+    return _pack(*out)
+
+
+def vmaxs2(a, b):
+    return _pack(*[max(x, y) for x, y in zip(_halves(a), _halves(b))])
+
+
+def vminu2(a, b):
+    return _pack(*[min(x & 0xFFFF, y & 0xFFFF) for x, y in zip(_halves(a), _halves(b))])
+
+
+def packed_general_scores(pair_a, pair_b, match, mismatch, first, nxt, local, affine):
+    """Two pairs of the same shape, one in each half, the cell update of the kernel's `cells` lambda row by row."""
+    (ra, ca), (rb, cb) = pair_a, pair_b
+    m, n = len(ra), len(ca)
+    assert (len(rb), len(cb)) == (m, n)
+    NEG2, floor2 = 0x80008000, pk_both(-32000)
+    first2, next2, match2, mismatch2 = pk_both(first), pk_both(nxt), pk_both(match), pk_both(mismatch)
+    add = lambda a, b: viaddmax_s16x2(a, b, NEG2)
+    Hprev = [pk_both(0 if (local or j == 0) else first + (j - 1) * nxt) for j in range(n + 1)]  # row 0
+    Eprev = [floor2] * (n + 1)
+    best = 0
+    for i in range(1, m + 1):
+        Hrow = [pk_both(0 if local else first + (i - 1) * nxt)] + [0] * n
+        Erow = [floor2] * (n + 1)
+        f = floor2
+        rc = ra[i - 1] | (rb[i - 1] << 16)
+        for j in range(1, n + 1):
+            cc = ca[j - 1] | (cb[j - 1] << 16)
+            ne = vminu2(rc ^ cc, 0x00010001)
+            mask = (ne * 0xFFFF) & M32
+            s = (mask & mismatch2) | (~mask & M32 & match2)
+            if affine:
+                e = viaddmax_s16x2(Eprev[j], next2, add(Hprev[j], first2))
+                f = viaddmax_s16x2(f, next2, add(Hrow[j - 1], first2))
+                h = vmaxs2(viaddmax_s16x2(Hprev[j - 1], s, e), f)
+                Erow[j] = e
+            else:
+                h = vmaxs2(viaddmax_s16x2(Hprev[j - 1], s, add(Hrow[j - 1], next2)), add(Hprev[j], next2))
+            if local:
+                h = vmaxs2(h, 0)
+                best = vmaxs2(best, h)
+            Hrow[j] = h
+        Hprev, Eprev = Hrow, Erow
+    return _halves(best) if local else _halves(Hprev[n])
+
+
+@pytest.mark.parametrize("local", [False, True])
+@pytest.mark.parametrize("first,nxt", [(-2, -2), (-5, -1), (-6, -1)])
+def test_packed_s16x2_alignment_cells(local, first, nxt):
+    rng = random.Random(first * 7 + nxt + local)
+    affine = first != nxt
+    sub = lambda x, y: 2 if x == y else -1
+    for _ in range(25):
+        m, n = rng.randint(1, 24), rng.randint(1, 40)
+        mk = lambda k: bytes(rng.choice(b"ACGT") for _ in range(k))
+        pa, pb = (mk(m), mk(n)), (mk(m), mk(n))
+        got = packed_general_scores(pa, pb, 2, -1, first, nxt, local, affine)
+        want = (pyref.align_score(pa[0], pa[1], sub, first, nxt, local), pyref.align_score(pb[0], pb[1], sub, first, nxt, local))
+        assert tuple(got) == want, (pa, pb)
+
+
+def test_packed_range_precondition_keeps_sums_inside_int16():
+    """engine.cu routes a batch to the packed kernel only if Q = 3*first + (m+n)*min(next, mismatch) > -28000 and
+    min(m,n)*match < 32000. Every H is at least the all-gaps score 2*first + (m+n)*min(next, mismatch) = Q - first, so
+    with costs of int8 magnitude no add of the cell update can leave int16, not even from the gap tracks' floor."""
+    floor = -32000
+    for first, nxt, mismatch, match in itertools.product((-128, -12, -5, -2, 0), (-128, -3, -1, 0), (-128, -4, -1, 0), (0, 2, 127)):
+        lo_cost = min(nxt, mismatch)
+        if lo_cost == 0:
+            continue
+        total = (-28000 - 3 * first) // lo_cost  # the largest m + n the precondition admits (lo_cost < 0: floor division rounds towards it)
+        while 3 * first + total * lo_cost <= -28000:
+            total -= 1
+        if total < 2:
+            continue
+        h_min = 2 * first + total * lo_cost
+        h_max = 31999 if match == 0 else min(31999, (32000 // match) * match)
+        for a, b in ((floor, nxt), (h_min, first), (h_min, nxt), (h_min, mismatch), (h_max, match), (floor, first)):
+            assert -32768 <= a + b <= 32767, (first, nxt, mismatch, match, a, b)
