@@ -53,6 +53,8 @@ for cls, local in ((sw.NeedlemanWunschScores, False), (sw.SmithWatermanScores, T
         print(f"{cls.__name__} ({o},{e}): {'ok' if np.array_equal(got, want) else 'MISMATCH'} ({eng.last_kernel})", flush=True)
 q = datasets.words_pairs(80)[0]
 check("cross", lev.compute(scope, q.subview(0, 40), q.subview(40, 80)), orc.levenshtein_cross(q.data, q.offsets[:41], q.data, q.offsets[40:81]))
+q = datasets.words_pairs(1200)[0]  # large enough for the table-reusing cross kernel (tile-buffered result rows)
+check("cross (table reuse)", lev.compute(scope, q.subview(0, 512), q.subview(512, 1152)), orc.levenshtein_cross(q.data, q.offsets[:513], q.data, q.offsets[512:1153]))
 import torch
 dev = torch.device("cuda", 0)
 a, b = datasets.ascii_pairs(1000, 64)
