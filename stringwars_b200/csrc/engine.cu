@@ -1063,9 +1063,9 @@ extern "C" swb_status_t swb_compute_pairs(swb_engine_t *engine, const uint8_t *a
         // (d_a_offs is already biased by -lo, so +lo lands on the first uploaded element).
         SWB_CUDA(cudaStreamWaitEvent(ctx.compute_stream, ctx.ev_offsets, 0));
         if ((st = enqueue_schedule_count(ctx, sh.ps, ctx.compute_stream, err)) != SWB_OK) return st;
-        // data in ~8 MiB chunks so compute on chunk i overlaps the copy of chunk i+1
+        // data in ~16 MiB chunks so compute on chunk i overlaps the copy of chunk i+1
         const uint64_t bytes = (a_hi - a_lo) + (b_hi - b_lo);
-        static const uint64_t chunk_mb = getenv("SWB_CHUNK_MB") ? std::max(1, atoi(getenv("SWB_CHUNK_MB"))) : 8;
+        static const uint64_t chunk_mb = getenv("SWB_CHUNK_MB") ? std::max(1, atoi(getenv("SWB_CHUNK_MB"))) : 16; // measured 2/4/8/16/32 MiB: 1.22/1.38/1.45/1.49/1.45 TCUPS e2e at 64x64
         int chunks = (int)std::min<uint64_t>(64, std::max<uint64_t>(1, bytes / (chunk_mb << 20)));
         sh.chunk_cut.assign(chunks + 1, sh.lo);
         sh.chunk_cut[chunks] = sh.hi;
