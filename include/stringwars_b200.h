@@ -43,7 +43,8 @@ typedef enum swb_status_t {
     SWB_NO_DEVICE = 3,     /* no usable CUDA device / device ordinal out of range */
     SWB_CUDA_ERROR = 4,    /* a CUDA runtime call or kernel failed; message carries cudaGetErrorString */
     SWB_TOO_LONG = 5,      /* an input string exceeds what the selected kernel supports */
-    SWB_UNSUPPORTED = 6    /* feature not built into this library */
+    SWB_UNSUPPORTED = 6,   /* feature not built into this library */
+    SWB_NCCL_ERROR = 7     /* libnccl could not be loaded, or an NCCL call of the multi-GPU scatter / gather failed */
 } swb_status_t;
 
 /* Kernel family selection, see DESIGN.md. AUTO picks the fastest exact kernel for the cost model. */
@@ -82,6 +83,9 @@ SWB_API uint64_t swb_launch_count(void);
 /* `DeviceScope::gpu_device(0)` (bench.rs:379). `num_devices` > 1 makes every host-pointer call shard its
  * batch over devices [first_device, first_device + num_devices) by contiguous pair ranges balanced on cells. */
 SWB_API swb_status_t swb_scope_create(int first_device, int num_devices, swb_scope_t **out, const char **err);
+/* Same, over an explicit list of device ordinals. An ordinal may repeat: every entry gets its own streams and
+ * scratch, so a one-GPU box exercises the whole multi-device sharding path (`<{n}gpu>` variants, bench.rs:498-501). */
+SWB_API swb_status_t swb_scope_create_devices(const int *devices, int num_devices, swb_scope_t **out, const char **err);
 SWB_API void swb_scope_destroy(swb_scope_t *scope);
 SWB_API int swb_scope_num_devices(const swb_scope_t *scope);
 
@@ -91,6 +95,11 @@ SWB_API int swb_scope_num_devices(const swb_scope_t *scope);
  * allocated here make the host-pointer calls copy at full PCIe rate. Ordinary malloc'd memory also works. */
 SWB_API swb_status_t swb_host_alloc(size_t bytes, void **out, const char **err);
 SWB_API void swb_host_free(void *ptr);
+/* The reference's allocator itself: CUDA managed memory (`UnifiedAlloc`, bench.rs:292; `UnifiedMat`, bench.rs:130).
+ * Tapes and matrices allocated here are used by the `_view` calls IN PLACE (no staging copy): pages migrate to the
+ * device on first touch and stay there until the host touches them again. */
+SWB_API swb_status_t swb_unified_alloc(size_t bytes, void **out, const char **err);
+SWB_API void swb_unified_free(void *ptr);
 
 /* ---- engines ------------------------------------------------------------------------------------------- */
 
@@ -171,6 +180,70 @@ SWB_API swb_status_t swb_compute_cross_device(swb_engine_t *engine, int device_i
                                               const uint64_t *q_offsets, size_t n_queries, const uint8_t *c_data,
                                               const uint64_t *c_offsets, size_t n_candidates, uint64_t *out,
                                               size_t row_stride, void *cuda_stream, const char **err);
+
+/* ---- typed tape views, result widths, resident tapes ----------------------------------------------------
+ * The reference hands its engines `AnyBytesTape::View64(view)` (bench.rs:141-142): an enum over offset widths,
+ * over a tape that lives in CUDA managed memory (`BytesTape<u64, UnifiedAlloc>`, bench.rs:292-295), and a
+ * `UnifiedMat` result matrix (bench.rs:130) that the device writes in place. `swb_tape_view_t` is that enum as
+ * a plain struct, and the `_view` calls below accept ANY memory for every pointer — each is classified with
+ * cudaPointerGetAttributes:
+ *   pageable / page-locked host   staged: chunk-pipelined H2D copies (tape) / device staging + D2H (results);
+ *   managed (cudaMallocManaged)   used in place, no copy: pages migrate on first touch and then stay resident,
+ *                                 exactly like the reference's tape after its first call;
+ *   device (cudaMalloc)           used in place on the owning device (it must be a device of the scope).
+ * Results may be narrower than the ABI's usize / isize: a Levenshtein distance below 65,536 fits u16, an
+ * alignment score fits i32; four times fewer bytes cross PCIe when the matrix lives in host memory. Values that
+ * do not fit are truncated to the low bits (two's complement), so pick a width that holds them. */
+typedef struct swb_tape_view_t {
+    const uint8_t *data;  /* base of the byte buffer the offsets index into */
+    const void *offsets;  /* n + 1 monotonically non-decreasing offsets, u64 or u32 (offset_bits) */
+    size_t n;             /* number of strings */
+    int offset_bits;      /* 64 or 32 */
+} swb_tape_view_t;
+
+typedef enum swb_result_type_t {
+    SWB_RESULT_64 = 0, /* u64 distances / i64 scores: `UnifiedMat<usize>` / `UnifiedMat<isize>` (bench.rs:130, 193) */
+    SWB_RESULT_32 = 1, /* u32 / i32 */
+    SWB_RESULT_16 = 2  /* u16 / i16 */
+} swb_result_type_t;
+
+/* swb_compute_pairs / swb_compute_cross over typed views, any memory kind, any result width (blocking). */
+SWB_API swb_status_t swb_compute_pairs_view(swb_engine_t *engine, const swb_tape_view_t *a, const swb_tape_view_t *b,
+                                            void *out, swb_result_type_t out_type, const char **err);
+SWB_API swb_status_t swb_compute_cross_view(swb_engine_t *engine, const swb_tape_view_t *queries,
+                                            const swb_tape_view_t *candidates, void *out, size_t row_stride,
+                                            swb_result_type_t out_type, const char **err);
+
+/* Resident tapes: upload once, compute many times — what `BytesTape<u64, UnifiedAlloc>` gives the reference after
+ * the first touch (bench.rs:292-306; the timing loop at bench.rs:587-605 never copies). The tape is copied to
+ * every device of the scope (a cross product needs all candidates everywhere; pairs are sharded by range).
+ * `first` / `n` select a sub-range like `BytesTapeView::subview(lo, hi)` (bench.rs:134-139). */
+typedef struct swb_tape swb_tape_t;
+SWB_API swb_status_t swb_tape_upload(swb_scope_t *scope, const swb_tape_view_t *view, swb_tape_t **out, const char **err);
+SWB_API void swb_tape_destroy(swb_tape_t *tape);
+SWB_API size_t swb_tape_len(const swb_tape_t *tape);
+/* Device view of strings [first, first + n) of the tape's copy on scope device `device_index` (device pointers). */
+SWB_API swb_status_t swb_tape_device_view(const swb_tape_t *tape, int device_index, size_t first, size_t n,
+                                          swb_tape_view_t *out, const char **err);
+SWB_API swb_status_t swb_compute_pairs_tape(swb_engine_t *engine, const swb_tape_t *a, size_t a_first, const swb_tape_t *b,
+                                            size_t b_first, size_t n_pairs, void *out, swb_result_type_t out_type,
+                                            const char **err);
+SWB_API swb_status_t swb_compute_cross_tape(swb_engine_t *engine, const swb_tape_t *queries, size_t q_first, size_t n_queries,
+                                            const swb_tape_t *candidates, size_t c_first, size_t n_candidates, void *out,
+                                            size_t row_stride, swb_result_type_t out_type, const char **err);
+
+/* ---- multi-GPU: one NCCL scatter, per-device kernels, one NCCL gather (BASELINE.json north_star) ---------
+ * `LevenshteinDistances<{n}gpu>` (multi-GPU variant naming, bench.rs:498-501) for a batch that is RESIDENT ON THE
+ * SCOPE'S FIRST DEVICE: both views and `out` are device memory of scope device 0 (the root). The library owns a
+ * single-process NCCL communicator over the scope's devices (ncclCommInitAll, created on first use; libnccl is
+ * loaded at run time). The pair range is cut into contiguous shards balanced by bytes; every shard travels in
+ * chunks — grouped ncclSend / ncclRecv of the tape slice and of u32 offsets rebuilt relative to the slice — and each
+ * chunk's kernel starts as soon as it has landed, while the next chunk is still on NVLink; results return to `out`
+ * on the root the same way. The root's own shard never moves. Blocking.
+ * `stats`, when non-NULL, receives {scatter bytes sent by the root, gather bytes received by the root,
+ * device ms from first send to last result (root clock), 0}. */
+SWB_API swb_status_t swb_compute_pairs_scatter(swb_engine_t *engine, const swb_tape_view_t *a, const swb_tape_view_t *b,
+                                               void *out, swb_result_type_t out_type, double stats[4], const char **err);
 
 /* Pair-load phase only: stages every pair's bytes through shared memory with the same coalesced 16-byte
  * loads the compute kernels use and writes a byte-sum per pair. Exists so the HBM-read rate of the load

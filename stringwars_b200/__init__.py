@@ -7,9 +7,10 @@ and fails loudly if it is missing or no GPU is present — there is no CPU fallb
 from ._lib import Error, LIB_PATH  # noqa: F401
 from .szs import (  # noqa: F401
     ALGO_AUTO, ALGO_BITPARALLEL, ALGO_WAVEFRONT, GAP_BIO, GAP_STRINGZILLA,
-    DeviceScope, LevenshteinDistances, LevenshteinDistancesUtf8, NeedlemanWunschScores, SmithWatermanScores,
+    DeviceScope, DeviceTape, LevenshteinDistances, LevenshteinDistancesUtf8, NeedlemanWunschScores, SmithWatermanScores,
     device_count, launch_count, multiprocessor_count, unary_class_costs,
 )
-from .tape import BytesTape, PinnedBuffer, unified_mat  # noqa: F401
+from ._lib import RESULT_16, RESULT_32, RESULT_64, TapeView  # noqa: F401
+from .tape import BytesTape, ManagedBuffer, PinnedBuffer, unified_mat  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -13,6 +13,14 @@ c_u64p = ctypes.POINTER(ctypes.c_uint64)
 c_i8p = ctypes.POINTER(ctypes.c_int8)
 c_err = ctypes.POINTER(ctypes.c_char_p)
 
+class TapeView(ctypes.Structure):
+    """`swb_tape_view_t`: AnyBytesTape::View64 / View32 as a plain struct (bench.rs:141-142)."""
+    _fields_ = [("data", ctypes.c_void_p), ("offsets", ctypes.c_void_p), ("n", ctypes.c_size_t), ("offset_bits", ctypes.c_int)]
+
+
+c_viewp = ctypes.POINTER(TapeView)
+RESULT_64, RESULT_32, RESULT_16 = 0, 1, 2
+
 # every symbol include/stringwars_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "swb_version": (ctypes.c_int, []),
@@ -24,6 +32,21 @@ SIGNATURES = {
     "swb_scope_num_devices": (ctypes.c_int, [ctypes.c_void_p]),
     "swb_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), c_err]),
     "swb_host_free": (None, [ctypes.c_void_p]),
+    "swb_unified_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), c_err]),
+    "swb_unified_free": (None, [ctypes.c_void_p]),
+    "swb_scope_create_devices": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), c_err]),
+    "swb_compute_pairs_view": (ctypes.c_int, [ctypes.c_void_p, c_viewp, c_viewp, ctypes.c_void_p, ctypes.c_int, c_err]),
+    "swb_compute_cross_view": (ctypes.c_int, [ctypes.c_void_p, c_viewp, c_viewp, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, c_err]),
+    "swb_tape_upload": (ctypes.c_int, [ctypes.c_void_p, c_viewp, ctypes.POINTER(ctypes.c_void_p), c_err]),
+    "swb_tape_destroy": (None, [ctypes.c_void_p]),
+    "swb_tape_len": (ctypes.c_size_t, [ctypes.c_void_p]),
+    "swb_tape_device_view": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, c_viewp, c_err]),
+    "swb_compute_pairs_tape": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                              ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, c_err]),
+    "swb_compute_cross_tape": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p,
+                                              ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, c_err]),
+    "swb_compute_pairs_scatter": (ctypes.c_int, [ctypes.c_void_p, c_viewp, c_viewp, ctypes.c_void_p, ctypes.c_int,
+                                                 ctypes.POINTER(ctypes.c_double), c_err]),
     "swb_levenshtein_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.POINTER(ctypes.c_void_p), c_err]),
     "swb_levenshtein_utf8_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -58,7 +81,7 @@ SIGNATURES = {
 }
 
 STATUS_NAMES = {0: "OK", 1: "BAD_ALLOC", 2: "INVALID_ARG", 3: "NO_DEVICE", 4: "CUDA_ERROR", 5: "TOO_LONG",
-                6: "UNSUPPORTED"}
+                6: "UNSUPPORTED", 7: "NCCL_ERROR"}
 
 _lib: Optional[ctypes.CDLL] = None
 

@@ -24,6 +24,7 @@
 // Reference semantics: `LevenshteinDistances` (bench.rs:382-393), `NeedlemanWunschScores` /
 // `SmithWatermanScores` with `unary_class_costs` tables (bench.rs:98-108, 655-674, 982-985).
 #pragma once
+#include "align_costs.h"
 #include "common.cuh"
 
 namespace swb {
@@ -31,18 +32,6 @@ namespace swb {
 constexpr int WF_THREADS = 128;
 constexpr int NEG_BIG = -(1 << 28);
 
-struct AlignCosts {
-    int match, mismatch; // unary path: S = classes equal ? match : mismatch
-    int first, next;     // gap costs (<= 0 in maximising form): length-k gap = first + (k-1)*next
-    int ident;           // 1: symbols are compared as raw bytes (no class map)
-    int negate;          // 1: write -H (Levenshtein distance)
-};
-
-struct AlignTables {
-    uint8_t byte_to_class[256];
-    int8_t costs[32 * 32];   // costs[class(a)][class(b)]
-    int8_t costs_t[32 * 32]; // transposed, used when the kernel swapped the pair so rows = shorter string
-};
 
 // G lanes per pair, R rows per lane. LOCAL: Smith-Waterman. AFFINE: Gotoh E/F tracks. UNARY: match/mismatch
 // constants instead of the 32x32 table. SymT: uint8_t symbols, or uint32_t for decoded UTF-8 (codepoint-level
@@ -237,7 +226,7 @@ __global__ void __launch_bounds__(WF_THREADS)
                 for (int r = 0; r < R; ++r)
                     if ((uint32_t)r == within % R) result = in_b ? HB[r] : HA[r];
                 if (SHIFTED) result += gap * (int)(m + n);
-                ps.out[out_index] = (uint64_t)(int64_t)(cs.negate ? -result : result);
+                store_result(ps, out_index, cs.negate ? -result : result);
             }
         }
         __syncwarp();
@@ -245,11 +234,11 @@ __global__ void __launch_bounds__(WF_THREADS)
     if (LOCAL) {
 #pragma unroll
         for (int d = G / 2; d >= 1; d >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, d, G));
-        if (have && lane == 0) ps.out[out_index] = (uint64_t)(int64_t)best;
+        if (have && lane == 0) store_result(ps, out_index, best);
     }
     if (have && !LOCAL && lane == 0 && m == 0) { // one side empty -> pure gap
         const int h = n == 0 ? 0 : cs.first + (int)(n - 1) * cs.next;
-        ps.out[out_index] = (uint64_t)(int64_t)(cs.negate ? -h : h);
+        store_result(ps, out_index, cs.negate ? -h : h);
     }
 }
 

@@ -157,16 +157,16 @@ __global__ void __launch_bounds__(WF_THREADS)
                     if ((uint32_t)r == within % R) packed = in_b ? HB[r] : HA[r];
                 const int shift = gap * (int)(m + n);
                 const int res_a = (int)(packed & 0xFFFFu) + shift, res_b = (int)(packed >> 16) + shift;
-                ps.out[out_index[0]] = (uint64_t)(int64_t)(cs.negate ? -res_a : res_a);
-                if (have_b) ps.out[out_index[1]] = (uint64_t)(int64_t)(cs.negate ? -res_b : res_b);
+                store_result(ps, out_index[0], cs.negate ? -res_a : res_a);
+                if (have_b) store_result(ps, out_index[1], cs.negate ? -res_b : res_b);
             }
         }
         __syncwarp();
     }
     if (have && lane == 0 && m == 0) { // one side empty -> pure gap
         const int h = n == 0 ? 0 : cs.first + (int)(n - 1) * cs.next;
-        ps.out[out_index[0]] = (uint64_t)(int64_t)(cs.negate ? -h : h);
-        if (have_b) ps.out[out_index[1]] = (uint64_t)(int64_t)(cs.negate ? -h : h);
+        store_result(ps, out_index[0], cs.negate ? -h : h);
+        if (have_b) store_result(ps, out_index[1], cs.negate ? -h : h);
     }
 }
 

@@ -208,8 +208,8 @@ __global__ void __launch_bounds__(WF_THREADS, (LOCAL ? 4 : 3))
                 for (int r = 0; r < R; ++r)
                     if ((uint32_t)r == within % R) packed = in_b ? HB[r] : HA[r];
                 const int res_a = pk::lo(packed), res_b = pk::hi(packed);
-                ps.out[out_index[0]] = (uint64_t)(int64_t)(cs.negate ? -res_a : res_a);
-                if (have_b) ps.out[out_index[1]] = (uint64_t)(int64_t)(cs.negate ? -res_b : res_b);
+                store_result(ps, out_index[0], cs.negate ? -res_a : res_a);
+                if (have_b) store_result(ps, out_index[1], cs.negate ? -res_b : res_b);
             }
         }
         __syncwarp();
@@ -218,14 +218,14 @@ __global__ void __launch_bounds__(WF_THREADS, (LOCAL ? 4 : 3))
 #pragma unroll
         for (int d = G / 2; d >= 1; d >>= 1) best = pk::max2(best, __shfl_xor_sync(0xffffffffu, best, d, G));
         if (have && lane == 0) {
-            ps.out[out_index[0]] = (uint64_t)(int64_t)pk::lo(best);
-            if (have_b) ps.out[out_index[1]] = (uint64_t)(int64_t)pk::hi(best);
+            store_result(ps, out_index[0], pk::lo(best));
+            if (have_b) store_result(ps, out_index[1], pk::hi(best));
         }
     }
     if (have && !LOCAL && lane == 0 && m == 0) { // one side empty -> pure gap
         const int h = n == 0 ? 0 : cs.first + (int)(n - 1) * cs.next;
-        ps.out[out_index[0]] = (uint64_t)(int64_t)(cs.negate ? -h : h);
-        if (have_b) ps.out[out_index[1]] = (uint64_t)(int64_t)(cs.negate ? -h : h);
+        store_result(ps, out_index[0], cs.negate ? -h : h);
+        if (have_b) store_result(ps, out_index[1], cs.negate ? -h : h);
     }
 }
 

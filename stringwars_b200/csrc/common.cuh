@@ -19,9 +19,26 @@ struct PairSpace {
     uint64_t n_c;          // 0: element-wise pairs; otherwise candidates per query
     uint64_t stride;       // cross mode: output row stride (elements)
     const uint32_t *order; // optional permutation (length-bucketed schedule); nullptr = identity
-    uint64_t *out;         // u64 distances or i64 scores
+    uint64_t *out;         // u64 distances or i64 scores (element width: out_narrow)
     uint32_t len_shift;    // log2(bytes per symbol): 0 for byte tapes, 2 for decoded UTF-8 (u32 symbols)
+    uint32_t out_narrow;   // 0: 64-bit results (the ABI's usize / isize); 1: 32-bit; 2: 16-bit (device staging that the host widens)
+    uint32_t offs32;       // bit 0: a_offs points at u32 offsets, bit 1: b_offs does (`BytesTapeView<u32>`, AnyBytesTape::View32)
 };
+
+// Offset i of tape A / B, whatever the offset width.
+__device__ __forceinline__ uint64_t a_off(const PairSpace &ps, uint64_t i) {
+    return (ps.offs32 & 1u) ? (uint64_t)reinterpret_cast<const uint32_t *>(ps.a_offs)[i] : ps.a_offs[i];
+}
+__device__ __forceinline__ uint64_t b_off(const PairSpace &ps, uint64_t i) {
+    return (ps.offs32 & 2u) ? (uint64_t)reinterpret_cast<const uint32_t *>(ps.b_offs)[i] : ps.b_offs[i];
+}
+
+// One result (distance or signed score) at element index `idx` of the output, in the width the host asked for.
+__device__ __forceinline__ void store_result(const PairSpace &ps, uint64_t idx, int64_t v) {
+    if (ps.out_narrow == 0u) ps.out[idx] = (uint64_t)v;
+    else if (ps.out_narrow == 1u) reinterpret_cast<uint32_t *>(ps.out)[idx] = (uint32_t)v;
+    else reinterpret_cast<uint16_t *>(ps.out)[idx] = (uint16_t)v;
+}
 
 struct PairView {
     const uint8_t *a, *b; // first byte of each string
@@ -45,8 +62,18 @@ __device__ __forceinline__ PairRequest pair_request(const PairSpace &ps, uint64_
         oi = ia * ps.stride + ib;
     }
     PairRequest r;
-    r.a0 = ps.a_offs[ia], r.a1 = ps.a_offs[ia + 1];
-    r.b0 = ps.b_offs[ib], r.b1 = ps.b_offs[ib + 1];
+    if (ps.offs32 & 1u) {
+        const uint32_t *a32 = reinterpret_cast<const uint32_t *>(ps.a_offs);
+        r.a0 = a32[ia], r.a1 = a32[ia + 1];
+    } else {
+        r.a0 = ps.a_offs[ia], r.a1 = ps.a_offs[ia + 1];
+    }
+    if (ps.offs32 & 2u) {
+        const uint32_t *b32 = reinterpret_cast<const uint32_t *>(ps.b_offs);
+        r.b0 = b32[ib], r.b1 = b32[ib + 1];
+    } else {
+        r.b0 = ps.b_offs[ib], r.b1 = ps.b_offs[ib + 1];
+    }
     r.out_index = oi;
     return r;
 }
@@ -55,8 +82,10 @@ __device__ __forceinline__ PairView pair_resolve(const PairSpace &ps, const Pair
     PairView v;
     v.a = ps.a_data + r.a0;
     v.b = ps.b_data + r.b0;
-    v.la = (uint32_t)((r.a1 - r.a0) >> ps.len_shift);
-    v.lb = (uint32_t)((r.b1 - r.b0) >> ps.len_shift);
+    // a string whose offsets run backwards reads as empty: the schedule kernel counts it and the host fails the call with
+    // SWB_INVALID_ARG, but a speculative kernel launched beside that check must not chase the wild length
+    v.la = r.a1 < r.a0 ? 0u : (uint32_t)((r.a1 - r.a0) >> ps.len_shift);
+    v.lb = r.b1 < r.b0 ? 0u : (uint32_t)((r.b1 - r.b0) >> ps.len_shift);
     v.out_index = r.out_index;
     return v;
 }

@@ -100,6 +100,8 @@ __device__ __forceinline__ void add_wide(const uint32_t (&a)[K], const uint32_t 
 template <int K>
 struct BitparConfig {
     static constexpr int THREADS = K <= 4 ? SWB_BITPAR_THREADS_SMALL : SWB_BITPAR_THREADS_K8; // 128 * K bytes of tables per thread; K = 8: 32 = 64 > 128
+    static constexpr int PAIRS_PER_THREAD = 1;
+    static constexpr size_t SMEM = (size_t)32 * THREADS * K * sizeof(uint32_t);
 };
 
 // Shared-memory layout of the nibble tables of a block of T threads with K words each.
@@ -321,7 +323,7 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
     const uint32_t m = swap ? pv.lb : pv.la;
     const uint32_t n = swap ? pv.la : pv.lb;
     if (m == 0) {
-        ps.out[pv.out_index] = n;
+        store_result(ps, pv.out_index, n);
         return;
     }
     if (m > 32u * K) return; // not this kernel's class (speculative launch on a batch that changed shape)
@@ -447,7 +449,7 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
     uint32_t score = n;
 #pragma unroll
     for (int w = 0; w < K; ++w) score += __popc(Pv[w]) - __popc(Mv[w]);
-    ps.out[pv.out_index] = score;
+    store_result(ps, pv.out_index, score);
 }
 
 } // namespace swb

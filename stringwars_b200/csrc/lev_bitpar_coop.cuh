@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(BPC_THREADS)
     }
 #pragma unroll
     for (int d = G / 2; d >= 1; d >>= 1) delta_sum += __shfl_xor_sync(0xffffffffu, delta_sum, d, G);
-    if (have && lane == G - 1) ps.out[out_index] = (uint64_t)((int64_t)n + delta_sum);
+    if (have && lane == G - 1) store_result(ps, out_index, (int64_t)n + delta_sum);
 }
 
 } // namespace swb

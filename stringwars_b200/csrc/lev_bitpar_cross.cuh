@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(CrossConfig<K>::THREADS)
     uint32_t m = 0;
     const uint8_t *pat = nullptr;
     if (have) {
-        const uint64_t o0 = ps.a_offs[q], o1 = ps.a_offs[q + 1];
+        const uint64_t o0 = a_off(ps, q), o1 = a_off(ps, q + 1);
         pat = ps.a_data + o0;
         m = (uint32_t)(o1 - o0);
     }
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(CrossConfig<K>::THREADS)
     const bool active = have && fits && m > 0;
 
     for (uint32_t c = c_lo; c < c_hi; ++c) {
-        const uint64_t b0 = ps.b_offs[c], b1 = ps.b_offs[c + 1];
+        const uint64_t b0 = b_off(ps, c), b1 = b_off(ps, c + 1);
         const uint8_t *txt = ps.b_data + b0;
         const uint32_t n = (uint32_t)(b1 - b0);
         uint32_t Pv[K], Mv[K];
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(CrossConfig<K>::THREADS)
                 const uint32_t qq = q_block + row;
                 const uint32_t v = tile[row * TILE_PITCH + col];
                 // rows of queries that do not fit this kernel's K are left untouched (the host never sends them here)
-                if (col < width && qq < n_queries && v != 0xFFFFFFFFu) ps.out[(uint64_t)qq * ps.stride + c_first + col] = v;
+                if (col < width && qq < n_queries && v != 0xFFFFFFFFu) store_result(ps, (uint64_t)qq * ps.stride + c_first + col, v);
             }
             __syncthreads();
         }

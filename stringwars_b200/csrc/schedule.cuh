@@ -20,6 +20,7 @@ struct ScheduleStats {
     uint32_t max_m[SCHED_MCLASSES];
     uint32_t max_n[SCHED_MCLASSES];
     uint32_t min_m, min_n;
+    uint32_t bad;     // strings whose offsets run backwards or span 2^32 bytes or more: the call fails with SWB_INVALID_ARG
     uint32_t ticket;  // blocks that have merged their counters (device copy only)
     uint32_t seq;     // host copy only: sequence number of the call whose counters are complete
 };
@@ -35,22 +36,37 @@ __device__ __forceinline__ int key_of(uint32_t m, uint32_t n) {
     return mclass_of(m) * SCHED_NBINS + (int)bin;
 }
 
+#ifdef SWB_SCHEDULE_KERNELS // plain (non-template) kernels: defined in exactly one translation unit, pipeline.cu
+
 // `stats` (device) must be all-zero with min_* = 0xFFFFFFFF on entry; the LAST block to finish publishes the
 // merged counters into `published` (mapped, page-locked host memory: no D2H copy, no event — the host polls
 // `published->seq`) and restores `stats` to its entry state for the next call.
-__global__ void __launch_bounds__(256) schedule_count_kernel(PairSpace ps, ScheduleStats *stats, ScheduleStats *published, uint32_t seq) {
+//
+// The kernel is also the offsets validator the ABI promises (SWB_INVALID_ARG for non-monotonic offsets): it reads every
+// offset of both tapes anyway, so a string whose end lies before its start (or 4 GiB or more after it) is counted in
+// `bad` instead of being keyed, and the host refuses the batch before any compute kernel sees it. `extra_offs`
+// (optional) is a second offsets array of extra_n + 1 entries checked the same way — the candidate tape of a cross
+// product whose statistics are taken over the queries alone.
+__global__ void __launch_bounds__(256) schedule_count_kernel(PairSpace ps, ScheduleStats *stats, ScheduleStats *published, uint32_t seq,
+                                                             const void *extra_offs, uint64_t extra_n, uint32_t extra32) {
     __shared__ uint32_t s_counts[SCHED_KEYS];
     __shared__ uint32_t s_max_m[SCHED_MCLASSES], s_max_n[SCHED_MCLASSES];
-    __shared__ uint32_t s_min_m, s_min_n;
+    __shared__ uint32_t s_min_m, s_min_n, s_bad;
     __shared__ bool s_last;
     for (int i = threadIdx.x; i < SCHED_KEYS; i += blockDim.x) s_counts[i] = 0;
     if (threadIdx.x < SCHED_MCLASSES) s_max_m[threadIdx.x] = 0, s_max_n[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_min_m = 0xFFFFFFFFu, s_min_n = 0xFFFFFFFFu;
+    if (threadIdx.x == 0) s_min_m = 0xFFFFFFFFu, s_min_n = 0xFFFFFFFFu, s_bad = 0u;
     __syncthreads();
     // Threads keep a run (key, count, extrema) in registers and touch shared memory only when the key changes;
     // a warp whose lanes all ended on the same key merges with warp reductions and ONE set of atomics. Uniform
     // batches (every pair the same key) would otherwise serialise a million atomics on a single counter.
     int run_key = -1;
+    uint32_t bad = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < extra_n && extra_offs; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t o0 = extra32 ? (uint64_t)reinterpret_cast<const uint32_t *>(extra_offs)[i] : reinterpret_cast<const uint64_t *>(extra_offs)[i];
+        const uint64_t o1 = extra32 ? (uint64_t)reinterpret_cast<const uint32_t *>(extra_offs)[i + 1] : reinterpret_cast<const uint64_t *>(extra_offs)[i + 1];
+        if (o1 < o0 || ((o1 - o0) >> 32) != 0u) ++bad;
+    }
     uint32_t run_count = 0, run_max_m = 0, run_max_n = 0, run_min_m = 0xFFFFFFFFu, run_min_n = 0xFFFFFFFFu;
     auto flush = [&](int key, uint32_t count, uint32_t mx_m, uint32_t mx_n, uint32_t mn_m, uint32_t mn_n) {
         if (key < 0) return;
@@ -64,7 +80,12 @@ __global__ void __launch_bounds__(256) schedule_count_kernel(PairSpace ps, Sched
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < ps.n_pairs; k += (uint64_t)gridDim.x * blockDim.x) {
         PairSpace id = ps;
         id.order = nullptr;
-        const PairView pv = pair_at(id, k);
+        const PairRequest rq = pair_request(id, k);
+        if (rq.a1 < rq.a0 || rq.b1 < rq.b0 || ((rq.a1 - rq.a0) >> 32) != 0u || ((rq.b1 - rq.b0) >> 32) != 0u) {
+            ++bad;
+            continue;
+        }
+        const PairView pv = pair_resolve(id, rq);
         const uint32_t m = min(pv.la, pv.lb), n = max(pv.la, pv.lb);
         const int key = key_of(m, n);
         if (key != run_key) {
@@ -86,6 +107,7 @@ __global__ void __launch_bounds__(256) schedule_count_kernel(PairSpace ps, Sched
             flush(run_key, run_count, run_max_m, run_max_n, run_min_m, run_min_n);
         }
     }
+    if (bad) atomicAdd(&s_bad, bad);
     __syncthreads();
     for (int i = threadIdx.x; i < SCHED_KEYS; i += blockDim.x)
         if (s_counts[i]) atomicAdd(&stats->counts[i], s_counts[i]);
@@ -96,6 +118,7 @@ __global__ void __launch_bounds__(256) schedule_count_kernel(PairSpace ps, Sched
     if (threadIdx.x == 0) {
         atomicMin(&stats->min_m, s_min_m);
         atomicMin(&stats->min_n, s_min_n);
+        if (s_bad) atomicAdd(&stats->bad, s_bad);
     }
     __threadfence();
     __syncthreads();
@@ -115,7 +138,8 @@ __global__ void __launch_bounds__(256) schedule_count_kernel(PairSpace ps, Sched
     }
     if (threadIdx.x == 0) {
         published->min_m = vs->min_m, published->min_n = vs->min_n;
-        stats->min_m = 0xFFFFFFFFu, stats->min_n = 0xFFFFFFFFu, stats->ticket = 0;
+        published->bad = vs->bad;
+        stats->min_m = 0xFFFFFFFFu, stats->min_n = 0xFFFFFFFFu, stats->bad = 0, stats->ticket = 0;
     }
     __threadfence_system();
     __syncthreads();
@@ -214,7 +238,7 @@ __global__ void __launch_bounds__(LOAD_THREADS) load_phase_kernel(PairSpace ps, 
     }
     auto issue = [&](uint64_t tile, int stage) { // thread 0 only
         const uint64_t p0 = tile * tile_pairs, p1 = min(p0 + (uint64_t)tile_pairs, ps.n_pairs);
-        const uint64_t a_lo = ps.a_offs[p0], a_hi = ps.a_offs[p1], b_lo = ps.b_offs[p0], b_hi = ps.b_offs[p1];
+        const uint64_t a_lo = a_off(ps, p0), a_hi = a_off(ps, p1), b_lo = b_off(ps, p0), b_hi = b_off(ps, p1);
         const uint8_t *ga = ps.a_data + a_lo, *gb = ps.b_data + b_lo;
         const uint32_t mis_a = (uint32_t)(reinterpret_cast<uintptr_t>(ga) & 15u), mis_b = (uint32_t)(reinterpret_cast<uintptr_t>(gb) & 15u);
         // whole 16-byte pieces covering each span: exactly what the compute kernels' staging loads touch
@@ -236,7 +260,7 @@ __global__ void __launch_bounds__(LOAD_THREADS) load_phase_kernel(PairSpace ps, 
         const uint64_t p0 = tile * tile_pairs, p1 = min(p0 + (uint64_t)tile_pairs, ps.n_pairs);
         const uint64_t p = p0 + threadIdx.x;
         uint64_t oa0 = 0, oa1 = 0, ob0 = 0, ob1 = 0;
-        if (p < p1) oa0 = ps.a_offs[p], oa1 = ps.a_offs[p + 1], ob0 = ps.b_offs[p], ob1 = ps.b_offs[p + 1];
+        if (p < p1) oa0 = a_off(ps, p), oa1 = a_off(ps, p + 1), ob0 = b_off(ps, p), ob1 = b_off(ps, p + 1);
         {
             uint32_t done = 0;
             const uint32_t parity = (it >> 1) & 1u;
@@ -264,7 +288,7 @@ __global__ void __launch_bounds__(LOAD_THREADS) load_phase_simple_kernel(PairSpa
     uint8_t *s_a = lsm, *s_b = lsm + cap_a;
     const uint64_t p0 = (uint64_t)blockIdx.x * tile_pairs;
     const uint64_t p1 = min(p0 + (uint64_t)tile_pairs, ps.n_pairs);
-    const uint64_t a_lo = ps.a_offs[p0], a_hi = ps.a_offs[p1], b_lo = ps.b_offs[p0], b_hi = ps.b_offs[p1];
+    const uint64_t a_lo = a_off(ps, p0), a_hi = a_off(ps, p1), b_lo = b_off(ps, p0), b_hi = b_off(ps, p1);
     const uint8_t *ga = ps.a_data + a_lo, *gb = ps.b_data + b_lo;
     const uint32_t mis_a = (uint32_t)(reinterpret_cast<uintptr_t>(ga) & 15u), mis_b = (uint32_t)(reinterpret_cast<uintptr_t>(gb) & 15u);
     const uint32_t bytes_a = a_hi > a_lo ? ((mis_a + (uint32_t)(a_hi - a_lo) + 15u) & ~15u) : 0u;
@@ -278,7 +302,7 @@ __global__ void __launch_bounds__(LOAD_THREADS) load_phase_simple_kernel(PairSpa
     }
     const uint64_t p = p0 + threadIdx.x;
     uint64_t oa0 = 0, oa1 = 0, ob0 = 0, ob1 = 0;
-    if (p < p1) oa0 = ps.a_offs[p], oa1 = ps.a_offs[p + 1], ob0 = ps.b_offs[p], ob1 = ps.b_offs[p + 1];
+    if (p < p1) oa0 = a_off(ps, p), oa1 = a_off(ps, p + 1), ob0 = b_off(ps, p), ob1 = b_off(ps, p + 1);
     __syncthreads(); // mbarrier init visible to every thread before anyone waits on it
     {
         uint32_t done = 0;
@@ -292,5 +316,7 @@ __global__ void __launch_bounds__(LOAD_THREADS) load_phase_simple_kernel(PairSpa
         ps.out[p] = acc;
     }
 }
+
+#endif // SWB_SCHEDULE_KERNELS
 
 } // namespace swb

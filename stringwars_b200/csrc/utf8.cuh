@@ -12,14 +12,19 @@ namespace swb {
 
 // One warp per string: bytes_out[i + 1] = 4 * (number of symbols of string i); bytes_out[0] = 0.
 // `ascii_flag` is cleared (atomicAnd) when any byte >= 0x80 is seen.
-__global__ void __launch_bounds__(256) utf8_count_kernel(const uint8_t *data, const uint64_t *offs, uint64_t n_strings,
+__device__ __forceinline__ uint64_t tape_offset(const void *offs, uint32_t offs32, uint64_t i) {
+    return offs32 ? (uint64_t) reinterpret_cast<const uint32_t *>(offs)[i] : reinterpret_cast<const uint64_t *>(offs)[i];
+}
+
+__global__ void __launch_bounds__(256) utf8_count_kernel(const uint8_t *data, const void *offs, uint32_t offs32, uint64_t n_strings,
                                                          uint64_t *bytes_out, uint32_t *ascii_flag) {
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) bytes_out[0] = 0;
     if (warp >= n_strings) return;
-    const uint8_t *s = data + offs[warp];
-    const uint32_t len = (uint32_t)(offs[warp + 1] - offs[warp]);
+    const uint64_t o0 = tape_offset(offs, offs32, warp), o1 = tape_offset(offs, offs32, warp + 1);
+    const uint8_t *s = data + o0;
+    const uint32_t len = o1 < o0 ? 0u : (uint32_t)(o1 - o0);
     uint32_t count = 0;
     bool high = false;
     for (uint32_t p = lane; p < len; p += 32) {
@@ -34,13 +39,14 @@ __global__ void __launch_bounds__(256) utf8_count_kernel(const uint8_t *data, co
 }
 
 // One warp per string: writes the packed symbols of string i at symbols + sym_offs[i] / 4.
-__global__ void __launch_bounds__(256) utf8_pack_kernel(const uint8_t *data, const uint64_t *offs, uint64_t n_strings,
+__global__ void __launch_bounds__(256) utf8_pack_kernel(const uint8_t *data, const void *offs, uint32_t offs32, uint64_t n_strings,
                                                         const uint64_t *sym_offs, uint32_t *symbols) {
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= n_strings) return;
-    const uint8_t *s = data + offs[warp];
-    const uint32_t len = (uint32_t)(offs[warp + 1] - offs[warp]);
+    const uint64_t o0 = tape_offset(offs, offs32, warp), o1 = tape_offset(offs, offs32, warp + 1);
+    const uint8_t *s = data + o0;
+    const uint32_t len = o1 < o0 ? 0u : (uint32_t)(o1 - o0);
     uint32_t *out = symbols + (sym_offs[warp] >> 2);
     uint32_t written = 0;
     for (uint32_t base = 0; base < len; base += 32) {

@@ -24,6 +24,8 @@ import numpy as np
 from . import _lib
 from .tape import BytesTape, TapeLike, as_tape, unified_mat
 
+_RESULT_TYPE = {8: _lib.RESULT_64, 4: _lib.RESULT_32, 2: _lib.RESULT_16}
+
 ALGO_AUTO, ALGO_WAVEFRONT, ALGO_BITPARALLEL = 0, 1, 2
 GAP_STRINGZILLA, GAP_BIO = 0, 1
 
@@ -47,12 +49,19 @@ def launch_count() -> int:
 class DeviceScope:
     """`szs::DeviceScope`. Only GPU scopes exist; `cpu_cores` raises (no CPU path in this library)."""
 
-    def __init__(self, first_device: int = 0, num_devices: int = 1):
+    def __init__(self, first_device: int = 0, num_devices: int = 1, devices=None):
         self._h = ctypes.c_void_p()
         err = ctypes.c_char_p()
-        _lib.check(_lib.lib().swb_scope_create(first_device, num_devices, ctypes.byref(self._h), ctypes.byref(err)), err)
+        if devices is not None:
+            devices = [int(d) for d in devices]
+            arr = (ctypes.c_int * len(devices))(*devices)
+            _lib.check(_lib.lib().swb_scope_create_devices(arr, len(devices), ctypes.byref(self._h), ctypes.byref(err)), err)
+            first_device, num_devices = (devices[0] if devices else 0), len(devices)
+        else:
+            _lib.check(_lib.lib().swb_scope_create(first_device, num_devices, ctypes.byref(self._h), ctypes.byref(err)), err)
         self.first_device, self.num_devices = first_device, num_devices
         self._engines = weakref.WeakSet()  # engines hold device state owned by the scope: they are closed first
+        self._tapes = weakref.WeakSet()
 
     @classmethod
     def gpu_device(cls, device: int = 0) -> "DeviceScope":
@@ -63,6 +72,16 @@ class DeviceScope:
         return cls(first_device, num_devices)
 
     @classmethod
+    def device_list(cls, devices) -> "DeviceScope":
+        """Explicit ordinals; an ordinal may repeat (one GPU then plays several devices of the sharding path)."""
+        return cls(devices=list(devices))
+
+    def upload(self, tape: TapeLike) -> "DeviceTape":
+        """Resident copy of a tape on every device of the scope (what `UnifiedAlloc` gives the reference after the
+        first touch): later `compute_*` calls on it move no input bytes."""
+        return DeviceTape(self, as_tape(tape))
+
+    @classmethod
     def cpu_cores(cls, _count: int) -> "DeviceScope":
         raise _lib.Error(6, "stringwars_b200 has no CPU engines; use a GPU scope")
 
@@ -70,6 +89,8 @@ class DeviceScope:
         if self._h:
             for engine in list(self._engines):
                 engine.close()
+            for tape in list(self._tapes):
+                tape.close()
             _lib.lib().swb_scope_destroy(self._h)
             self._h = ctypes.c_void_p()
 
@@ -82,6 +103,56 @@ class DeviceScope:
 
 def _ptr(arr: np.ndarray) -> int:
     return arr.ctypes.data
+
+
+class DeviceTape:
+    """`swb_tape_t`: a tape uploaded once to every device of a scope. `subview(lo, hi)` is a zero-copy range of it."""
+
+    def __init__(self, scope: DeviceScope, tape: BytesTape, _parent: "DeviceTape" = None, _lo: int = 0, _hi: int = None):
+        self._scope = scope
+        if _parent is not None:
+            self._root, self._h, self.lo, self.hi = _parent._root, _parent._h, _lo, _hi
+            return
+        self._root = self
+        self._h = ctypes.c_void_p()
+        err = ctypes.c_char_p()
+        view = tape.view()
+        _lib.check(_lib.lib().swb_tape_upload(scope._h, ctypes.byref(view), ctypes.byref(self._h), ctypes.byref(err)), err)
+        self.lo, self.hi = 0, len(tape)
+        scope._tapes.add(self)
+
+    def __len__(self) -> int:
+        return self.hi - self.lo
+
+    def subview(self, lo: int, hi: int) -> "DeviceTape":
+        if not (0 <= lo <= hi <= len(self)):
+            raise IndexError(f"subview [{lo}, {hi}) outside tape of {len(self)}")
+        return DeviceTape(self._scope, None, _parent=self, _lo=self.lo + lo, _hi=self.lo + hi)
+
+    def device_view(self, device_index: int = 0) -> "_lib.TapeView":
+        view = _lib.TapeView()
+        err = ctypes.c_char_p()
+        _lib.check(_lib.lib().swb_tape_device_view(self._root._h, device_index, self.lo, len(self), ctypes.byref(view), ctypes.byref(err)), err)
+        return view
+
+    def close(self) -> None:
+        if self._root is self and self._h:
+            _lib.lib().swb_tape_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _check_out(out: np.ndarray, base_dtype, n: int) -> int:
+    """Results may be narrower than usize / isize (`swb_result_type_t`): same signedness, 8 / 4 / 2 bytes."""
+    kind = np.dtype(base_dtype).kind
+    if out.dtype.kind != kind or out.dtype.itemsize not in _RESULT_TYPE or out.size < n or not out.flags.c_contiguous:
+        raise ValueError(f"out must be a contiguous {'unsigned' if kind == 'u' else 'signed'} 64/32/16-bit array of >= {n} elements")
+    return _RESULT_TYPE[out.dtype.itemsize]
 
 
 class _Engine:
@@ -120,42 +191,65 @@ class _Engine:
         return (_lib.lib().swb_engine_last_kernel(self._h) or b"").decode()
 
     # ---- host tapes
-    def compute_pairs(self, scope: DeviceScope, a: TapeLike, b: TapeLike, out: Optional[np.ndarray] = None) -> np.ndarray:
-        """out[i] = score(a[i], b[i]) — the batched form of `(a:&[u8], b:&[u8]) -> usize` (bench.rs:416-419)."""
-        ta, tb = as_tape(a), as_tape(b)
+    def compute_pairs(self, scope: DeviceScope, a, b, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """out[i] = score(a[i], b[i]) — the batched form of `(a:&[u8], b:&[u8]) -> usize` (bench.rs:416-419).
+        `a` / `b`: BytesTape (any memory, u64 or u32 offsets), sequences of strings, or DeviceTape (resident)."""
+        resident = isinstance(a, DeviceTape) or isinstance(b, DeviceTape)
+        if resident and not (isinstance(a, DeviceTape) and isinstance(b, DeviceTape)):
+            raise ValueError("either both tapes are resident (DeviceTape) or neither")
+        ta, tb = (a, b) if resident else (as_tape(a), as_tape(b))
         if len(ta) != len(tb):
             raise ValueError(f"tapes differ in length: {len(ta)} vs {len(tb)}")
         n = len(ta)
         if out is None:
             out = np.zeros(n, dtype=self.out_dtype)
-        if out.dtype != self.out_dtype or out.size < n or not out.flags.c_contiguous:
-            raise ValueError(f"out must be a contiguous {np.dtype(self.out_dtype).name} array of >= {n} elements")
+        rtype = _check_out(out, self.out_dtype, n)
         err = ctypes.c_char_p()
-        da = ta.data if ta.data.size else np.zeros(1, np.uint8)
-        db = tb.data if tb.data.size else np.zeros(1, np.uint8)
-        _lib.check(_lib.lib().swb_compute_pairs(self._h, _ptr(da), _ptr(ta.offsets), _ptr(db), _ptr(tb.offsets), n,
-                                                _ptr(out), ctypes.byref(err)), err)
+        if resident:
+            _lib.check(_lib.lib().swb_compute_pairs_tape(self._h, ta._root._h, ta.lo, tb._root._h, tb.lo, n, _ptr(out), rtype,
+                                                         ctypes.byref(err)), err)
+        else:
+            va, vb = ta.view(), tb.view()
+            _lib.check(_lib.lib().swb_compute_pairs_view(self._h, ctypes.byref(va), ctypes.byref(vb), _ptr(out), rtype, ctypes.byref(err)), err)
         return out
 
-    def compute_into(self, scope: DeviceScope, queries: TapeLike, candidates: Optional[TapeLike], matrix: np.ndarray) -> None:
+    def compute_into(self, scope: DeviceScope, queries, candidates, matrix: np.ndarray) -> None:
         """`engine.compute_into(&scope, queries, Some(candidates), &mut matrix)` (bench.rs:599-603)."""
-        tq = as_tape(queries)
-        tc = tq if candidates is None else as_tape(candidates)
+        resident = isinstance(queries, DeviceTape)
+        tq = queries if resident else as_tape(queries)
+        tc = tq if candidates is None else (candidates if isinstance(candidates, DeviceTape) else as_tape(candidates))
+        if resident != isinstance(tc, DeviceTape):
+            raise ValueError("either both tapes are resident (DeviceTape) or neither")
         nq, nc = len(tq), len(tc)
-        if matrix.dtype != self.out_dtype or matrix.ndim != 2 or matrix.shape[0] < nq or matrix.shape[1] < nc:
-            raise ValueError(f"matrix must be {np.dtype(self.out_dtype).name} with shape >= ({nq}, {nc})")
+        kind = np.dtype(self.out_dtype).kind
+        if matrix.dtype.kind != kind or matrix.dtype.itemsize not in _RESULT_TYPE or matrix.ndim != 2 or matrix.shape[0] < nq or matrix.shape[1] < nc:
+            raise ValueError(f"matrix must be a 64/32/16-bit {'unsigned' if kind == 'u' else 'signed'} array with shape >= ({nq}, {nc})")
         if matrix.strides[1] != matrix.itemsize or matrix.strides[0] % matrix.itemsize:
             raise ValueError("matrix rows must be contiguous")
+        rtype = _RESULT_TYPE[matrix.dtype.itemsize]
+        stride = matrix.strides[0] // matrix.itemsize
         err = ctypes.c_char_p()
-        dq = tq.data if tq.data.size else np.zeros(1, np.uint8)
-        dc = tc.data if tc.data.size else np.zeros(1, np.uint8)
-        _lib.check(_lib.lib().swb_compute_cross(self._h, _ptr(dq), _ptr(tq.offsets), nq, _ptr(dc), _ptr(tc.offsets), nc,
-                                                _ptr(matrix), matrix.strides[0] // matrix.itemsize, ctypes.byref(err)), err)
+        if resident:
+            _lib.check(_lib.lib().swb_compute_cross_tape(self._h, tq._root._h, tq.lo, nq, tc._root._h, tc.lo, nc, _ptr(matrix), stride, rtype,
+                                                         ctypes.byref(err)), err)
+        else:
+            vq, vc = tq.view(), tc.view()
+            _lib.check(_lib.lib().swb_compute_cross_view(self._h, ctypes.byref(vq), ctypes.byref(vc), _ptr(matrix), stride, rtype,
+                                                         ctypes.byref(err)), err)
+
+    def compute_pairs_scatter(self, a_view: "_lib.TapeView", b_view: "_lib.TapeView", out_ptr: int, result_type: int = _lib.RESULT_64):
+        """`LevenshteinDistances<{n}gpu>` over a batch resident on the scope's first device: one NCCL scatter, per-device
+        kernels, one NCCL gather (swb_compute_pairs_scatter). Returns {sent_bytes, gathered_bytes, device_ms, chunks}."""
+        stats = (ctypes.c_double * 4)()
+        err = ctypes.c_char_p()
+        _lib.check(_lib.lib().swb_compute_pairs_scatter(self._h, ctypes.byref(a_view), ctypes.byref(b_view), out_ptr, result_type, stats,
+                                                        ctypes.byref(err)), err)
+        return {"sent_bytes": int(stats[0]), "gathered_bytes": int(stats[1]), "device_ms": float(stats[2]), "chunks": int(stats[3])}
 
     def compute(self, scope: DeviceScope, queries: TapeLike, candidates: Optional[TapeLike] = None) -> np.ndarray:
         """`engine.compute(&scope, &queries, &candidates) -> UnifiedMat` (bench.rs:587-589): allocates the matrix."""
-        tq = as_tape(queries)
-        tc = tq if candidates is None else as_tape(candidates)
+        tq = queries if isinstance(queries, DeviceTape) else as_tape(queries)
+        tc = tq if candidates is None else (candidates if isinstance(candidates, DeviceTape) else as_tape(candidates))
         matrix = unified_mat(len(tq), len(tc), self.out_dtype)
         self.compute_into(scope, tq, tc, matrix)
         return matrix

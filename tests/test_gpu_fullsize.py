@@ -1,6 +1,6 @@
-"""BASELINE.json's full sizes on the GPU. The oracle cannot finish 1M x 256x256 in seconds on a test budget, so
-full-size parity is established by (i) size-independent properties and (ii) bit-exact oracle checks on large
-random samples of the full batch."""
+"""BASELINE.json's full sizes on the GPU: every pair of every full-size batch is checked bit-exact against the oracle
+(the rapidfuzz-class family finishes 1M x 256x256 in about a second on the box's cores), next to size-independent
+properties (symmetry, identity, both kernel families agreeing, checksum of chunked calls)."""
 import numpy as np
 import pytest
 
@@ -18,12 +18,10 @@ def ctx():
     scope.close()
 
 
-def _sample_check(oracle, a, b, got, k=40_000, seed=0):
-    idx = np.sort(np.random.default_rng(seed).choice(len(a), size=min(k, len(a)), replace=False))
-    sa = BytesTape.from_strings([a[int(i)] for i in idx[:4000]])
-    sb = BytesTape.from_strings([b[int(i)] for i in idx[:4000]])
-    want = oracle.levenshtein_pairs(sa.data, sa.offsets, sb.data, sb.offsets, oracle.RAPIDFUZZ_CLASS, threads=16)
-    assert np.array_equal(got[idx[:4000]], want)
+def _full_check(oracle, a, b, got):
+    want = oracle.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, oracle.RAPIDFUZZ_CLASS, threads=32)
+    bad = np.flatnonzero(got != want)
+    assert bad.size == 0, f"{bad.size} of {len(a)} pairs differ from the oracle, first {bad[:5]}"
 
 
 @pytest.mark.parametrize("length", [64, 256])
@@ -42,10 +40,8 @@ def test_one_million_pairs(ctx, oracle, length):
     wf = lev.set_algorithm(sw.ALGO_WAVEFRONT).compute_pairs(scope, a, b)
     lev.set_algorithm(sw.ALGO_AUTO)
     assert np.array_equal(d_ab, wf)
-    # oracle on a random sample + on the first 20k pairs
-    _sample_check(oracle, a, b, d_ab)
-    head = oracle.levenshtein_pairs(a.data, a.offsets[:20_001], b.data, b.offsets[:20_001], oracle.RAPIDFUZZ_CLASS, threads=16)
-    assert np.array_equal(d_ab[:20_000], head)
+    # the oracle on ALL 2^20 pairs
+    _full_check(oracle, a, b, d_ab)
     # checksum-of-checksums: chunked calls give the same total as one call
     total = int(d_ab.sum())
     parts = sum(int(lev.compute_pairs(scope, a.subview(lo, lo + n // 8), b.subview(lo, lo + n // 8)).sum()) for lo in range(0, n, n // 8))
@@ -59,7 +55,7 @@ def test_config3_full_100k_utf8_lines(ctx, oracle):
     la, lb = a.lengths().astype(np.int64), b.lengths().astype(np.int64)
     assert (d.astype(np.int64) >= np.abs(la - lb)).all() and (d.astype(np.int64) <= np.maximum(la, lb)).all()
     assert np.array_equal(d, lev.compute_pairs(scope, b, a))
-    _sample_check(oracle, a, b, d, seed=1)
+    _full_check(oracle, a, b, d)
 
 
 def test_config5_full_nw_10k_acgt(ctx, oracle):
@@ -71,5 +67,5 @@ def test_config5_full_nw_10k_acgt(ctx, oracle):
         got = nw.compute_pairs(scope, a, b)
         assert np.array_equal(got, nw.compute_pairs(scope, b, a))            # symmetric costs => symmetric score
         assert (got <= 2 * 1024).all() and (got >= -3 * 2048).all()
-        want = oracle.align_pairs(a.data, a.offsets[:601], b.data, b.offsets[:601], btc, costs, open_, extend, threads=16)
-        assert np.array_equal(got[:600], want)
+        want = oracle.align_pairs(a.data, a.offsets, b.data, b.offsets, btc, costs, open_, extend, threads=32)  # all 10k pairs
+        assert np.array_equal(got, want)
