@@ -331,7 +331,7 @@ extern "C" swb_status_t swb_engine_set_algorithm(swb_engine_t *engine, swb_algor
     if (algorithm == SWB_ALGO_BITPARALLEL && engine->kind != ENGINE_LEVENSHTEIN && engine->kind != ENGINE_LEVENSHTEIN_UTF8)
         return fail(err, SWB_INVALID_ARG, "the bit-parallel kernel only exists for unit-cost Levenshtein");
     engine->algorithm = algorithm;
-    engine->spec_class = -1;
+    engine->spec_class = 0;
     return SWB_OK;
 }
 

@@ -137,6 +137,7 @@ struct swb_engine {
     swb::AlignTables tables;
     std::vector<swb::AlignTables *> d_tables; // per device
     const char *last_kernel = "none";
+    uint32_t spec_max_n = 0; // longest text of that batch: the speculative kernel skips anything longer (unvalidated lengths)
     int spec_class = 0; // kernel code (launch_lev_bitpar's K) of the last uniform batch on the device-resident path; 0: do not speculate
     bool profiling = false;
     std::vector<ProfEvents> prof_events; // pool
@@ -200,8 +201,9 @@ swb_status_t check_engine_alive(swb_engine *engine, const char **err);
 // launch_lev.cu: one length class of byte Levenshtein by the bit-vector kernels (any pattern length).
 swb_status_t launch_lev_class(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count, uint32_t max_m,
                               uint32_t max_n, cudaStream_t stream, const char **err);
-// thread-per-pair kernel of word count K = 1, 2, 4, 8 over the whole pair space (the speculative launch)
-swb_status_t launch_lev_bitpar(swb_engine *eng, DeviceCtx &ctx, int K, const PairSpace &ps, uint64_t begin, uint64_t count,
+// thread-per-pair kernel of word count K = 1, 2, 4, 8 (or the register kernel of -K pattern words) over the whole pair
+// space — the speculative launch; pairs whose longer string exceeds n_cap are skipped
+swb_status_t launch_lev_bitpar(swb_engine *eng, DeviceCtx &ctx, int K, const PairSpace &ps, uint64_t begin, uint64_t count, uint32_t n_cap,
                                cudaStream_t stream, const char **err);
 // cross product with per-query table reuse; max_q <= 256
 swb_status_t launch_lev_cross(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint32_t n_queries, uint32_t cands_per_block,

@@ -13,14 +13,14 @@ namespace swb {
 
 template <int K>
 static swb_status_t launch_bitpar(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count,
-                                  cudaStream_t stream, const char **err) {
+                                  cudaStream_t stream, const char **err, uint32_t n_cap = 0xFFFFFFFFu) {
     constexpr int T = BitparConfig<K>::THREADS;
     const size_t smem = BitparConfig<K>::SMEM;
     SWB_CUDA(allow_smem((const void *)lev_bitpar_kernel<K>, ctx.device, smem));
     const uint64_t blocks = (count + (uint64_t)T * BitparConfig<K>::PAIRS_PER_THREAD - 1) / ((uint64_t)T * BitparConfig<K>::PAIRS_PER_THREAD);
     {
         ProfileBracket bracket(eng, ctx.device, stream);
-        lev_bitpar_kernel<K><<<(unsigned)blocks, T, smem, stream>>>(ps, begin, count);
+        lev_bitpar_kernel<K><<<(unsigned)blocks, T, smem, stream>>>(ps, begin, count, n_cap);
     }
     g_launches++;
     static const char *names[] = {"", "lev_bitpar<K=1>", "lev_bitpar<K=2>", "", "lev_bitpar<K=4>", "", "", "", "lev_bitpar<K=8>"};
@@ -32,11 +32,11 @@ static swb_status_t launch_bitpar(swb_engine *eng, DeviceCtx &ctx, const PairSpa
 // Patterns of at most 32 bytes with the pattern's match masks derived in registers (lev_short.cuh): no tables.
 template <int W>
 static swb_status_t launch_short(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count,
-                                 cudaStream_t stream, const char **err) {
+                                 cudaStream_t stream, const char **err, uint32_t n_cap = 0xFFFFFFFFu) {
     const uint64_t blocks = (count + SHORT_THREADS - 1) / SHORT_THREADS;
     {
         ProfileBracket bracket(eng, ctx.device, stream);
-        lev_short_kernel<W><<<(unsigned)blocks, SHORT_THREADS, 0, stream>>>(ps, begin, count);
+        lev_short_kernel<W><<<(unsigned)blocks, SHORT_THREADS, 0, stream>>>(ps, begin, count, n_cap);
     }
     g_launches++;
     eng->last_kernel = W == 2 ? "lev_short<W=2>" : (W == 4 ? "lev_short<W=4>" : "lev_short<W=6>");
@@ -95,17 +95,17 @@ static swb_status_t launch_bitpar_cross(swb_engine *eng, DeviceCtx &ctx, const P
     return SWB_OK;
 }
 
-swb_status_t launch_lev_bitpar(swb_engine *eng, DeviceCtx &ctx, int K, const PairSpace &ps, uint64_t begin, uint64_t count,
+swb_status_t launch_lev_bitpar(swb_engine *eng, DeviceCtx &ctx, int K, const PairSpace &ps, uint64_t begin, uint64_t count, uint32_t n_cap,
                                cudaStream_t stream, const char **err) {
     // K <= 0 selects the register kernel of -K pattern words
     switch (K) {
-    case -2: return launch_short<2>(eng, ctx, ps, begin, count, stream, err);
-    case -4: return launch_short<4>(eng, ctx, ps, begin, count, stream, err);
-    case -6: return launch_short<6>(eng, ctx, ps, begin, count, stream, err);
-    case 1: return launch_bitpar<1>(eng, ctx, ps, begin, count, stream, err);
-    case 2: return launch_bitpar<2>(eng, ctx, ps, begin, count, stream, err);
-    case 4: return launch_bitpar<4>(eng, ctx, ps, begin, count, stream, err);
-    case 8: return launch_bitpar<8>(eng, ctx, ps, begin, count, stream, err);
+    case -2: return launch_short<2>(eng, ctx, ps, begin, count, stream, err, n_cap);
+    case -4: return launch_short<4>(eng, ctx, ps, begin, count, stream, err, n_cap);
+    case -6: return launch_short<6>(eng, ctx, ps, begin, count, stream, err, n_cap);
+    case 1: return launch_bitpar<1>(eng, ctx, ps, begin, count, stream, err, n_cap);
+    case 2: return launch_bitpar<2>(eng, ctx, ps, begin, count, stream, err, n_cap);
+    case 4: return launch_bitpar<4>(eng, ctx, ps, begin, count, stream, err, n_cap);
+    case 8: return launch_bitpar<8>(eng, ctx, ps, begin, count, stream, err, n_cap);
     }
     return fail(err, SWB_INVALID_ARG, "no bit-vector kernel of %d words", K);
 }

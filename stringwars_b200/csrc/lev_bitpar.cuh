@@ -297,7 +297,7 @@ __device__ __forceinline__ void add_symbol(uint32_t base, uint32_t pos, uint32_t
 // what lets the host launch this kernel speculatively, before the batch's length statistics are known — the
 // statistics then tell the host whether anything was skipped (engine.cu, run_device_batch).
 template <int K>
-__global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(PairSpace ps, uint64_t begin, uint64_t count) {
+__global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(PairSpace ps, uint64_t begin, uint64_t count, uint32_t n_cap) {
     constexpr int T = BitparConfig<K>::THREADS;
     using NT = NibbleTables<K, T>;
     extern __shared__ __align__(16) unsigned char tbl_bytes[]; // NibbleTables<K, T>::BYTES
@@ -326,7 +326,9 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
         store_result(ps, pv.out_index, n);
         return;
     }
-    if (m > 32u * K) return; // not this kernel's class (speculative launch on a batch that changed shape)
+    // not this kernel's class (speculative launch on a batch that changed shape), or a text longer than anything the
+    // host has validated (a speculative launch runs beside the offsets check: it must not chase an unchecked length)
+    if (m > 32u * K || n > n_cap) return;
     const uint32_t s = 32u * K - m; // pattern symbol i lives at bit position s + i
 
     // ---- requests that can leave before the tables are zeroed

@@ -88,7 +88,7 @@ __device__ __forceinline__ void short_columns(const uint32_t (&pat)[W], const ui
 
 // W = pattern words of the launch (the class's longest pattern): 2 (<= 8 bytes), 4 (<= 16), 6 (<= 24).
 template <int W>
-__global__ void __launch_bounds__(SHORT_THREADS) lev_short_kernel(PairSpace ps, uint64_t begin, uint64_t count) {
+__global__ void __launch_bounds__(SHORT_THREADS) lev_short_kernel(PairSpace ps, uint64_t begin, uint64_t count, uint32_t n_cap) {
     const uint64_t local = (uint64_t)blockIdx.x * SHORT_THREADS + threadIdx.x;
     if (local >= count) return;
     const uint32_t opaque0 = (uint32_t)(count >> 63); // run-time 0: see mad_lo in lev_bitpar.cuh
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(SHORT_THREADS) lev_short_kernel(PairSpace ps, 
         store_result(ps, pv.out_index, n);
         return;
     }
-    if (m > 4u * W) return; // not this kernel's class (the host picks W from the class's longest pattern)
+    if (m > 4u * W || n > n_cap) return; // not this kernel's class, or a length the host has not validated yet (speculative launch)
 
     // pattern: up to two 16-byte pieces, re-aligned in registers to start at its first byte
     PieceStream pat_stream, txt_stream;

@@ -184,7 +184,7 @@ swb_status_t swb::run_device_batch(swb_engine *eng, int dev_index, PairSpace ps,
     if (spec != 0) {
         SWB_CUDA(cudaEventRecord(ctx.ev_inputs, stream));
         SWB_CUDA(cudaStreamWaitEvent(ctx.side_stream, ctx.ev_inputs, 0));
-        if ((st = launch_lev_bitpar(eng, ctx, spec, ps, 0, ps.n_pairs, stream, err)) != SWB_OK) return st;
+        if ((st = launch_lev_bitpar(eng, ctx, spec, ps, 0, ps.n_pairs, eng->spec_max_n, stream, err)) != SWB_OK) return st;
         if ((st = enqueue_schedule_count(ctx, ps, ctx.side_stream, err)) != SWB_OK) return st;
     } else if ((st = enqueue_schedule_count(ctx, ps, stream, err)) != SWB_OK) {
         return st;
@@ -195,8 +195,9 @@ swb_status_t swb::run_device_batch(swb_engine *eng, int dev_index, PairSpace ps,
     Plan plan = make_plan(*ctx.h_stats);
     const bool uniform = plan.identity && plan.n_classes == 1;
     const int kernel_now = (uniform && lev_bytes) ? spec_kernel_of(plan) : 0;
-    eng->spec_class = kernel_now;
-    if (spec != 0 && kernel_now == spec) return SWB_OK; // the bet held: that kernel is the batch
+    const uint32_t spec_cap = eng->spec_max_n;
+    eng->spec_class = kernel_now, eng->spec_max_n = plan.n_classes ? plan.max_n[0] : 0u;
+    if (spec != 0 && kernel_now == spec && eng->spec_max_n <= spec_cap) return SWB_OK; // the bet held: that kernel is the batch
     if (!plan.identity && (st = enqueue_scatter(ctx, ps, stream, err)) != SWB_OK) return st;
     for (int i = 0; i < plan.n_classes; ++i) {
         st = launch_class(eng, ctx, dev_index, ps, plan.begin[i], plan.count[i], plan.max_m[i], plan.max_n[i], stream, err, plan.same_shape);
