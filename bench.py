@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — GCUPS of batched Levenshtein on B200 (BASELINE.json metric), one JSON line on stdout.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ascii64|ascii256]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ascii64|ascii256] [--no-gates]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one batch: every rank computes the distances of its own
@@ -13,7 +13,13 @@ A "step" is one pass of the hot path over one batch: every rank computes the dis
   roofline  HBM roofline of the dominant compute kernel: algorithmic bytes (len(a)+len(b) per pair,
             bench.rs:414) / kernel time from CUDA events recorded around that kernel on its launch stream.
   cpu_baseline  the oracle's rapidfuzz-class restatement timed on this box's host cores (bounded sample).
-`--impl reference` times that CPU restatement alone (the reference's own crates cannot be built here).
+  gates     (N = 1) the north-star gate and the other BASELINE.json configurations next to the main line: 1M length-256
+            pairs (value, e2e, CPU arm, every pair oracle-checked), the pair-load phase at 64 and 256 bytes, the
+            literal wavefront kernel, 1-core and textbook-DP CPU numbers, config 1 / 3 / 5, and the harness's own
+            cross-product shape on managed (`UnifiedAlloc`) and pinned memory beside the reference's published numbers.
+  config4   (N > 1) BASELINE.json configs[3] for real: N x 1.25M pairs of 256x256 resident on rank 0, scattered over
+            NVLink in chunks that overlap the kernels, gathered, and compared with the oracle on the FULL batch.
+`--impl reference` times the CPU restatement alone (the reference's own crates cannot be built here).
 torch is used for device memory, streams and torch.distributed only.
 """
 from __future__ import annotations
@@ -36,6 +42,8 @@ WORKLOADS = {
     "ascii64": (64, 1 << 20, "configs[1]: 1M random ASCII pairs 64x64"),
     "ascii256": (256, 1 << 20, "configs[3] per-GPU shard: 256x256 ASCII pairs (north_star parity gate: 1M length-256 pairs)"),
 }
+CFG4_PAIRS_PER_GPU = 1_250_000  # configs[3]: 10M pairs 256x256 over 8 GPUs
+NVLINK_EGRESS_GBS = 900.0       # NVLink 5, one direction, per GPU (the scatter leaves ONE GPU)
 
 
 def measured_peaks():
@@ -94,18 +102,400 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference(a, b, cells_per_pair: float, budget_s: float, threads: int):
-    """Times the oracle's rapidfuzz-class restatement (oracle/lev_oracle.c: orc_rf_lev_bytes) over a bounded
-    sample of the workload with `threads` host threads, timed inside C over enough repeats to fill
-    `budget_s`. Returns (gcups, pairs_processed, seconds)."""
+def cpu_reference(a, b, cells: float, budget_s: float, threads: int, kind=None):
+    """Times one family of the oracle (default: the rapidfuzz-class restatement, oracle/lev_oracle.c orc_rf_lev_bytes)
+    over a bounded sample of the workload with `threads` host threads, timed inside C over enough repeats to fill
+    `budget_s`. `cells` = DP cells of one pass over (a, b). Returns (gcups, pair evaluations, seconds)."""
     from oracle import oracle as orc
     orc.build()
+    kind = orc.RAPIDFUZZ_CLASS if kind is None else kind
     n = len(a)
-    secs, _ = orc.levenshtein_pairs_timed(a.data, a.offsets, b.data, b.offsets, orc.RAPIDFUZZ_CLASS, threads, 1)
+    secs, _ = orc.levenshtein_pairs_timed(a.data, a.offsets, b.data, b.offsets, kind, threads, 1)
     repeats = int(max(1, min(10_000, budget_s / max(secs, 1e-6))))
-    secs, _ = orc.levenshtein_pairs_timed(a.data, a.offsets, b.data, b.offsets, orc.RAPIDFUZZ_CLASS, threads, repeats)
-    return n * repeats * cells_per_pair / secs / 1e9, n * repeats, secs
+    if repeats > 1:
+        secs, _ = orc.levenshtein_pairs_timed(a.data, a.offsets, b.data, b.offsets, kind, threads, repeats)
+    return cells * repeats / secs / 1e9, n * repeats, secs
 
+
+def shared_config(workload: str, config_name: str, n_pairs: int, length: int):
+    """The `config` object of BOTH arms (ours and --impl reference): same keys, same values."""
+    return {"workload": f"{workload}: {config_name}", "pairs_per_gpu": n_pairs, "length": length,
+            "l2": "GPU arm: two input sets (2 x %.0f MB) rotated every step, larger than the 126 MB L2; CPU arm: a bounded sample of the same generator, "
+                  "repeated from host memory" % ((2.0 * length + 16.0) * n_pairs / 1e6),
+            "timing": "GPU arm: max(CUDA events on the launch stream, host wall) / steps, max over ranks; CPU arm: wall time inside C around the worker threads"}
+
+
+# ====================================================================================================== helpers (GPU)
+
+class Bench:
+    """Timing helpers bound to one rank's device, stream and process group."""
+
+    def __init__(self, torch, dist, device, world):
+        self.torch, self.dist, self.device, self.world = torch, dist, device, world
+        self.stream = torch.cuda.current_stream(device)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.device)
+
+    def timed(self, step_fn, steps):
+        """(device ms, wall ms) for `steps` calls, bracketed by barrier + synchronize on both sides."""
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(self.stream)
+        for i in range(steps):
+            step_fn(i)
+        e1.record(self.stream)
+        torch.cuda.synchronize(self.device)
+        wall = time.perf_counter() - t0
+        self.barrier()
+        return e0.elapsed_time(e1), wall * 1e3
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def per_call_ms(self, fn, min_calls=5, budget_s=0.5, warmup=2):
+        """Wall milliseconds per call of a BLOCKING function (median of the calls made inside the budget)."""
+        for _ in range(warmup):
+            fn()
+        self.torch.cuda.synchronize(self.device)
+        times, t_end = [], time.perf_counter() + budget_s
+        while len(times) < min_calls or (time.perf_counter() < t_end and len(times) < 2000):
+            t0 = time.perf_counter()
+            fn()
+            times.append((time.perf_counter() - t0) * 1e3)
+        return float(np.median(times)), len(times)
+
+
+def to_device_tape(torch, tape, device):
+    pad = torch.cat([torch.from_numpy(tape.data), torch.zeros(64, dtype=torch.uint8)]).to(device)
+    return pad, torch.from_numpy(tape.offsets.astype(np.int64)).to(device)
+
+
+def resident_value(bench, engine, dev_sets, n_pairs, d_out, steps, warmup):
+    """Device-resident GCUPS pieces: (ms per step, kernel ms per launch, launches, kernel name)."""
+    stream = bench.stream
+
+    def step(i):
+        ad, ao, bd, bo = dev_sets[i % len(dev_sets)]
+        engine.compute_pairs_device(ad.data_ptr(), ao.data_ptr(), bd.data_ptr(), bo.data_ptr(), n_pairs, d_out.data_ptr(), stream=stream.cuda_stream)
+
+    for i in range(warmup):
+        step(i)
+    engine.set_profiling(True)
+    dev_ms, wall_ms = bench.timed(step, steps)
+    kernel_ms, kernel_launches = engine.kernel_time()
+    engine.set_profiling(False)
+    return max(dev_ms, wall_ms) / steps, kernel_ms / max(kernel_launches, 1), kernel_launches, engine.last_kernel, step
+
+
+def load_phase(bench, engine, dev_sets, n_pairs, d_out, bytes_alg, peak):
+    stream = bench.stream
+    engine.set_profiling(True)
+    for i in range(8):
+        ad, ao, bd, bo = dev_sets[i % len(dev_sets)]
+        engine.load_phase_device(ad.data_ptr(), ao.data_ptr(), bd.data_ptr(), bo.data_ptr(), n_pairs, d_out.data_ptr(), stream=stream.cuda_stream)
+        if i == 2:
+            engine.kernel_time()
+    ms, n = engine.kernel_time()
+    engine.set_profiling(False)
+    gbs = bytes_alg / (ms / max(n, 1) * 1e-3) / 1e9 if ms > 0 else 0.0
+    return {"kernel": "load_phase_kernel", "achieved": gbs, "frac": gbs / peak, "ms": ms / max(n, 1)}
+
+
+# ====================================================================================================== gates (N = 1)
+
+def run_gates(bench, sw, datasets, scope, engine, args, peak, host_threads):
+    """The north-star gate and the remaining BASELINE.json configurations, each a few hundred milliseconds of GPU time."""
+    import torch
+    from oracle import oracle as orc
+    device, stream = bench.device, bench.stream
+    gates = {}
+
+    # ---- 1M length-256 pairs: value, e2e, roofline, CPU arm, EVERY pair checked against the oracle
+    n, L = 1 << 20, 256
+    a, b = datasets.ascii_pairs(n, L, seed=4242, pinned=True)
+    a2, b2 = datasets.ascii_pairs(n, L, seed=4243, pinned=True)
+    dev_sets = [(*to_device_tape(torch, a, device), *to_device_tape(torch, b, device)), (*to_device_tape(torch, a2, device), *to_device_tape(torch, b2, device))]
+    d_out = torch.zeros(n, dtype=torch.int64, device=device)
+    step_ms, kernel_ms, _, kernel, _ = resident_value(bench, engine, dev_sets, n, d_out, 10, 3)
+    cells = float(L) * L * n
+    host_sets = [(a, b), (a2, b2)]
+    h_out_buf = sw.PinnedBuffer(8 * n)  # the array below does not own the allocation: keep the buffer alive
+    h_out = h_out_buf.view(np.uint64)
+
+    def host_step(i):
+        x, y = host_sets[i & 1]
+        engine.compute_pairs(scope, x, y, out=h_out)
+
+    for i in range(2):
+        host_step(i)
+    _, e2e_wall = bench.timed(host_step, 6)
+    host_step(0)
+    t0 = time.perf_counter()
+    want = orc.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, orc.RAPIDFUZZ_CLASS, threads=host_threads)
+    oracle_s = time.perf_counter() - t0
+    parity_ok = bool(np.array_equal(h_out, want))
+    ad, ao, bd, bo = dev_sets[0]
+    engine.compute_pairs_device(ad.data_ptr(), ao.data_ptr(), bd.data_ptr(), bo.data_ptr(), n, d_out.data_ptr(), stream=stream.cuda_stream)
+    parity_ok = parity_ok and bool(np.array_equal(d_out.cpu().numpy().astype(np.uint64), want))
+    cpu_gcups, cpu_sample, cpu_dt = cpu_reference(a.subview(0, 1 << 17), b.subview(0, 1 << 17), float(L) * L * (1 << 17), 3.0, host_threads)
+    value = cells / (step_ms * 1e-3) / 1e9
+    e2e = cells / (e2e_wall / 6 * 1e-3) / 1e9
+    achieved = 2.0 * L * n / (kernel_ms * 1e-3) / 1e9
+    gates["ascii256_1M"] = {
+        "what": "north_star gate: bit-exact distances on 1M length-256 pairs at >= 10x the best CPU contender on 1 GPU",
+        "value": value, "e2e": e2e, "unit": "GCUPS", "kernel": kernel, "kernel_ms": kernel_ms, "ms_per_step": step_ms, "e2e_ms_per_step": e2e_wall / 6,
+        "roofline_frac": achieved / peak, "cpu_baseline": {"value": cpu_gcups, "cores": host_threads, "kind": "port", "sample": f"{cpu_sample} pair evaluations in {cpu_dt:.1f} s"},
+        "ratio": value / cpu_gcups, "e2e_ratio": e2e / cpu_gcups, "parity_pairs_checked": n, "parity_ok": parity_ok, "oracle_seconds": oracle_s}
+    gates["load_phase"] = {"ascii256": load_phase(bench, engine, dev_sets, n, d_out, 2.0 * L * n, peak)}
+
+    # ---- the literal north-star kernel (anti-diagonal wavefront) beside the kernel AUTO picks
+    engine.set_algorithm(sw.ALGO_WAVEFRONT)
+    wf_ms, _, _, wf_kernel, _ = resident_value(bench, engine, dev_sets, n, d_out, 3, 2)
+    gates["wavefront_gcups"] = {"ascii256": {"value": cells / (wf_ms * 1e-3) / 1e9, "kernel": wf_kernel}}
+    engine.set_algorithm(sw.ALGO_AUTO)
+    del dev_sets, d_out, h_out, h_out_buf, a2, b2
+    torch.cuda.empty_cache()
+
+    # ---- 64-byte strings: full-batch parity, wavefront kernel, 1-core and textbook-DP CPU numbers
+    n, L = 1 << 20, 64
+    a64, b64 = datasets.ascii_pairs(n, L, seed=42, pinned=True)
+    want = orc.levenshtein_pairs(a64.data, a64.offsets, b64.data, b64.offsets, orc.RAPIDFUZZ_CLASS, threads=host_threads)
+    got = engine.compute_pairs(scope, a64, b64)
+    dev64 = [(*to_device_tape(torch, a64, device), *to_device_tape(torch, b64, device))]
+    d_out = torch.zeros(n, dtype=torch.int64, device=device)
+    engine.set_algorithm(sw.ALGO_WAVEFRONT)
+    wf_ms, _, _, wf_kernel, _ = resident_value(bench, engine, dev64, n, d_out, 5, 2)
+    wf_ok = bool(np.array_equal(d_out.cpu().numpy().astype(np.uint64), want))
+    engine.set_algorithm(sw.ALGO_AUTO)
+    gates["wavefront_gcups"]["ascii64"] = {"value": float(L) * L * n / (wf_ms * 1e-3) / 1e9, "kernel": wf_kernel, "parity_ok": wf_ok}
+    gates["ascii64_1M_parity"] = {"parity_pairs_checked": n, "parity_ok": bool(np.array_equal(got, want))}
+    sa, sb = a64.subview(0, 1 << 16), b64.subview(0, 1 << 16)
+    c_small = float(L) * L * (1 << 16)
+    one_core, _, _ = cpu_reference(sa, sb, c_small, 1.5, 1)
+    bio_core, _, _ = cpu_reference(sa.subview(0, 1 << 13), sb.subview(0, 1 << 13), float(L) * L * (1 << 13), 1.5, 1, kind=orc.WAGNER_FISCHER)
+    all_core, _, _ = cpu_reference(sa, sb, c_small, 1.5, host_threads)
+    gates["cpu_64x64"] = {"unit": "GCUPS", "rapidfuzz_class_1core": one_core, "bio_class_textbook_dp_1core": bio_core, f"rapidfuzz_class_{host_threads}threads": all_core,
+                          "note": "the reference harness times its CPU contenders on one core (bench.rs:404-459); published 1xSPR: rapidfuzz 3.3 GCUPS at 100 B, bio 0.34"}
+    gates["load_phase"]["ascii64"] = load_phase(bench, engine, dev64, n, d_out, 2.0 * L * n, peak)
+    del dev64
+    torch.cuda.empty_cache()
+
+    # ---- config 1: words (<= 16 bytes). Pairs mode (G pairs/s) and the harness's cross product at its default batch.
+    n = 1 << 22
+    wa, wb = datasets.words_pairs(n, seed=7)
+    w_cells = float((wa.lengths().astype(np.float64) * wb.lengths().astype(np.float64)).sum())
+    w_bytes = float(wa.lengths().sum() + wb.lengths().sum())
+    dev_w = [(*to_device_tape(torch, wa, device), *to_device_tape(torch, wb, device))]
+    d_out = torch.zeros(n, dtype=torch.int64, device=device)
+    w_ms, w_kernel_ms, _, w_kernel, _ = resident_value(bench, engine, dev_w, n, d_out, 10, 3)
+    sample = slice(0, 1 << 18)
+    w_want = orc.levenshtein_pairs(wa.data, wa.offsets[: (1 << 18) + 1], wb.data, wb.offsets[: (1 << 18) + 1], orc.RAPIDFUZZ_CLASS, threads=host_threads)
+    gates["words_cfg1"] = {"pairs": n, "gpairs_per_s": n / (w_kernel_ms * 1e-3) / 1e9, "gcups": w_cells / (w_kernel_ms * 1e-3) / 1e9, "kernel": w_kernel, "kernel_ms": w_kernel_ms,
+                           "call_ms": w_ms, "hbm_frac_algorithmic": w_bytes / (w_kernel_ms * 1e-3) / 1e9 / peak,
+                           "parity_ok": bool(np.array_equal(d_out[sample].cpu().numpy().astype(np.uint64), w_want)), "parity_pairs_checked": 1 << 18}
+    del dev_w, d_out
+    torch.cuda.empty_cache()
+
+    # ---- the harness's own shape: side x side cross product (bench.rs:587-605), side = round(sqrt(batch_per_core * SMs))
+    sms = sw.multiprocessor_count(0)
+    sides = {"default_256_per_sm": int(round((256 * sms) ** 0.5)), "published_16384_per_sm": int(round((16384 * sms) ** 0.5))}
+    published = {"acgt_100": 5_980_110e-3, "acgt_1k": 6_237_990e-3, "words": 139_850e-3}  # GCUPS on 1x H100, similarities/README.md:38
+    harness = {"sms": sms, "sides": sides, "unit": "GCUPS", "published_h100_gcups": published,
+               "memory": {"managed": "tapes and matrix in cudaMallocManaged memory (the reference's UnifiedAlloc / UnifiedMat), used in place",
+                          "pinned_u64": "page-locked host tapes and u64 matrix, H2D + D2H inside every call",
+                          "pinned_u16": "same, results cross PCIe as u16 (swb_result_type_t)"}}
+    datasets_h = {"acgt_100": lambda k: datasets.acgt_pairs(k, 100, seed=11), "acgt_1k": lambda k: datasets.acgt_pairs(k, 1000, seed=12),
+                  "words": lambda k: datasets.words_pairs(k, seed=13)}
+    for name, gen in datasets_h.items():
+        entry = {}
+        for side_name, side in sides.items():
+            if name == "acgt_1k" and side > 600:
+                side = 600  # 1 KB lines: 600 x 600 x 10^6 cells already runs for tens of milliseconds
+            q, c = gen(side)
+            cells_x = float(np.outer(q.lengths().astype(np.float64), c.lengths().astype(np.float64)).sum())
+            ref = None
+            row = {"side": side}
+            for mem in ("managed", "pinned_u64", "pinned_u16"):
+                kind = "managed" if mem == "managed" else "pinned"
+                tq, tc = sw.BytesTape.from_arrays(q.data, q.offsets, memory=kind), sw.BytesTape.from_arrays(c.data, c.offsets, memory=kind)
+                m = sw.unified_mat(side, side, np.uint16 if mem == "pinned_u16" else np.uint64, memory=kind)
+                ms, calls = bench.per_call_ms(lambda: engine.compute_into(scope, tq, tc, m), budget_s=0.25)
+                row[mem] = {"gcups": cells_x / (ms * 1e-3) / 1e9, "ms_per_call": ms, "calls": calls}
+                if ref is None and side <= 400:
+                    ref = orc.levenshtein_cross(q.data, q.offsets, c.data, c.offsets, orc.RAPIDFUZZ_CLASS, threads=host_threads)
+                if ref is not None:
+                    row[mem]["parity_ok"] = bool(np.array_equal(np.asarray(m).astype(np.uint64), ref))
+            row["kernel"] = engine.last_kernel
+            entry[side_name] = row
+        harness[name] = entry
+    gates["harness_shape"] = harness
+
+    # ---- config 3 (UTF-8 lines, byte and code-point engines) and config 5 (NW, 10k x 1024)
+    la, lb = datasets.utf8_line_pairs(100_000, seed=3)
+    l_cells = float((la.lengths().astype(np.float64) * lb.lengths().astype(np.float64)).sum())
+    dev_l = [(*to_device_tape(torch, la, device), *to_device_tape(torch, lb, device))]
+    d_out = torch.zeros(len(la), dtype=torch.int64, device=device)
+    l_ms, _, _, l_kernel, _ = resident_value(bench, engine, dev_l, len(la), d_out, 5, 2)
+    l_want = orc.levenshtein_pairs(la.data, la.offsets, lb.data, lb.offsets, orc.RAPIDFUZZ_CLASS, threads=host_threads)
+    gates["utf8_lines_cfg3"] = {"bytes_engine": {"gcups": l_cells / (l_ms * 1e-3) / 1e9, "kernel": l_kernel, "parity_ok": bool(np.array_equal(d_out.cpu().numpy().astype(np.uint64), l_want)),
+                                                 "parity_pairs_checked": len(la)}}
+    utf8 = sw.LevenshteinDistancesUtf8(scope)
+    u_want = orc.levenshtein_pairs(la.data, la.offsets, lb.data, lb.offsets, orc.UTF8, threads=host_threads)
+    cp_a = np.add.reduceat(((la.data & 0xC0) != 0x80).astype(np.int64), la.offsets[:-1].astype(np.int64)).astype(np.float64)
+    cp_b = np.add.reduceat(((lb.data & 0xC0) != 0x80).astype(np.int64), lb.offsets[:-1].astype(np.int64)).astype(np.float64)
+    u_ms, _, _, u_kernel, _ = resident_value(bench, utf8, dev_l, len(la), d_out, 3, 2)
+    gates["utf8_lines_cfg3"]["codepoint_engine"] = {"gcups": float((cp_a * cp_b).sum()) / (u_ms * 1e-3) / 1e9, "kernel": u_kernel, "cells": "code points (bench.rs:612)",
+                                                    "parity_ok": bool(np.array_equal(d_out.cpu().numpy().astype(np.uint64), u_want)), "parity_pairs_checked": len(la)}
+    del dev_l
+    btc, costs = sw.unary_class_costs(2, -1)
+    na, nb = datasets.acgt_pairs(10_000, 1024, seed=5)
+    dev_n = [(*to_device_tape(torch, na, device), *to_device_tape(torch, nb, device))]
+    d_out = torch.zeros(len(na), dtype=torch.int64, device=device)
+    nw_entry = {}
+    for label, (op, ex) in {"linear": (-2, -2), "affine": (-5, -1)}.items():
+        nw = sw.NeedlemanWunschScores(scope, btc, costs, op, ex)
+        n_ms, _, _, n_kernel, _ = resident_value(bench, nw, dev_n, len(na), d_out, 3, 2)
+        n_want = orc.align_pairs(na.data, na.offsets[:1001], nb.data, nb.offsets[:1001], btc, costs, op, ex, threads=host_threads)
+        nw_entry[label] = {"gcups": 1024.0 * 1024.0 * len(na) / (n_ms * 1e-3) / 1e9, "kernel": n_kernel,
+                           "parity_ok": bool(np.array_equal(d_out[:1000].cpu().numpy(), n_want)), "parity_pairs_checked": 1000}
+    nw_entry["published_h100_gcups_acgt_1k"] = {"linear": 701.76, "affine": None}
+    gates["nw_cfg5"] = nw_entry
+    return gates
+
+
+# ====================================================================================================== config 4 (N > 1)
+
+def run_config4(bench, sw, datasets, scope, engine, rank, local_rank, world, host_threads):
+    """BASELINE.json configs[3]: world x 1.25M pairs of 256x256 (10M at N = 8), resident on rank 0, sharded over the
+    GPUs with one NCCL scatter and one gather, parity asserted against the oracle on the whole batch."""
+    import torch
+    import torch.distributed as dist
+    from stringwars_b200 import _lib, dist as swdist
+    device, stream = bench.device, bench.stream
+    L = 256
+    per_gpu = CFG4_PAIRS_PER_GPU
+    total = per_gpu * world
+    cells = float(L) * L * total
+    result = {"what": "configs[3]: %d pairs 256x256 resident on rank 0 -> chunked NCCL scatter overlapped with the kernels -> NCCL gather" % total,
+              "pairs": total, "length": L, "nvlink_egress_peak_gbs": NVLINK_EGRESS_GBS}
+    full_a = full_b = None
+    want = None
+    if rank == 0:
+        gen = torch.Generator(device=device)
+        gen.manual_seed(4)
+        ad = torch.randint(0x20, 0x7F, (total * L + 64,), dtype=torch.uint8, device=device, generator=gen)
+        bd = torch.randint(0x20, 0x7F, (total * L + 64,), dtype=torch.uint8, device=device, generator=gen)
+        offs = torch.arange(total + 1, dtype=torch.int64, device=device) * L
+        full_a, full_b = (ad, offs), (bd, offs.clone())
+        from oracle import oracle as orc
+        orc.build()
+        h_a, h_b, h_o = ad[: total * L].cpu().numpy(), bd[: total * L].cpu().numpy(), offs.cpu().numpy().astype(np.uint64)
+        t0 = time.perf_counter()
+        want = orc.levenshtein_pairs(h_a, h_o, h_b, h_o, orc.RAPIDFUZZ_CLASS, threads=host_threads)
+        result["oracle_seconds"] = time.perf_counter() - t0
+
+    def compute(a_data, a_offs, b_data, b_offs, out):
+        n_local = a_offs.numel() - 1
+        bits = 32 if a_offs.dtype == torch.int32 else 64
+        va = _lib.TapeView(a_data.data_ptr(), a_offs.data_ptr(), n_local, bits)
+        vb = _lib.TapeView(b_data.data_ptr(), b_offs.data_ptr(), n_local, bits)
+        engine.compute_pairs_device_view(va, vb, out.data_ptr(), _lib.RESULT_16, stream=stream.cuda_stream)
+
+    def noop(a_data, a_offs, b_data, b_offs, out):
+        pass
+
+    chunks = swdist.chunks_for(2 * total * L, world)
+    stats = {}
+    last = {}
+
+    def step(fn):
+        def run(i):
+            last["out"] = swdist.scatter_compute_gather(full_a, full_b, device, fn, total, torch.int16, chunks, stats=stats)
+        return run
+
+    for i in range(2):
+        step(compute)(i)
+    steps = 5
+    dev_ms, wall_ms = bench.timed(step(compute), steps)
+    ms = bench.max_over_ranks(max(dev_ms, wall_ms) / steps)
+    parity_ok = None
+    if rank == 0:
+        got = last["out"].cpu().numpy().astype(np.uint16).astype(np.uint64)
+        parity_ok = bool(np.array_equal(got, want))
+    dev_ms, wall_ms = bench.timed(step(noop), 3)
+    xfer_ms = bench.max_over_ranks(max(dev_ms, wall_ms) / 3)
+    result["nccl_multiprocess"] = {
+        "api": "stringwars_b200.dist.scatter_compute_gather (torch.distributed batch_isend_irecv = ncclGroupStart/End; one process per GPU)",
+        "gcups": cells / (ms * 1e-3) / 1e9, "ms_per_step": ms, "chunks_per_shard": chunks, "parity_ok": parity_ok, "parity_pairs_checked": total if rank == 0 else None,
+        "sent_bytes": stats.get("sent_bytes"), "gathered_bytes": stats.get("gathered_bytes"),
+        "nvlink_gbs": (stats.get("sent_bytes", 0) / (ms * 1e-3) / 1e9) if rank == 0 else None,
+        "nvlink_frac_of_egress": (stats.get("sent_bytes", 0) / (ms * 1e-3) / 1e9 / NVLINK_EGRESS_GBS) if rank == 0 else None,
+        "phases": {"scatter_gather_only_ms": xfer_ms, "scatter_only_nvlink_gbs": (stats.get("sent_bytes", 0) / (xfer_ms * 1e-3) / 1e9) if rank == 0 else None,
+                   "note": "scatter_gather_only = the same exchange with the kernels removed; the full step overlaps the two"}}
+    last.clear()
+
+    # ---- the same exchange inside the C ABI: ONE process (rank 0) drives all N GPUs through `swb_scope_create(0, N)`
+    bench.barrier()
+    if rank == 0 and sw.device_count() >= world:
+        try:
+            multi = sw.DeviceScope.gpu_devices(0, world)
+            lev = sw.LevenshteinDistances(multi)
+            out = torch.zeros(total, dtype=torch.int16, device=device)
+            va = _lib.TapeView(full_a[0].data_ptr(), full_a[1].data_ptr(), total, 64)
+            vb = _lib.TapeView(full_b[0].data_ptr(), full_b[1].data_ptr(), total, 64)
+            torch.cuda.synchronize(device)
+            for _ in range(2):
+                st = lev.compute_pairs_scatter(va, vb, out.data_ptr(), _lib.RESULT_16)
+            t0 = time.perf_counter()
+            dev_total = 0.0
+            for _ in range(5):
+                st = lev.compute_pairs_scatter(va, vb, out.data_ptr(), _lib.RESULT_16)
+                dev_total += st["device_ms"]
+            wall = (time.perf_counter() - t0) / 5 * 1e3
+            ok = bool(np.array_equal(out.cpu().numpy().astype(np.uint16).astype(np.uint64), want))
+            result["nccl_in_library"] = {
+                "api": "swb_compute_pairs_scatter: single process, ncclCommInitAll over the scope's devices (LevenshteinDistances<%dgpu>, bench.rs:498-501)" % world,
+                "gcups": cells / (wall * 1e-3) / 1e9, "ms_per_step": wall, "device_ms": dev_total / 5, "chunks_per_shard": st["chunks"], "parity_ok": ok,
+                "parity_pairs_checked": total, "sent_bytes": st["sent_bytes"], "nvlink_gbs": st["sent_bytes"] / (wall * 1e-3) / 1e9,
+                "nvlink_frac_of_egress": st["sent_bytes"] / (wall * 1e-3) / 1e9 / NVLINK_EGRESS_GBS}
+            del out
+            # ---- and the harness's starting point: the whole batch in HOST memory, one call over the N-GPU scope
+            h_a = sw.PinnedBuffer(total * L + 64)
+            h_b = sw.PinnedBuffer(total * L + 64)
+            h_a.array[: total * L] = full_a[0][: total * L].cpu().numpy()
+            h_b.array[: total * L] = full_b[0][: total * L].cpu().numpy()
+            h_o_buf, h_out_buf = sw.PinnedBuffer(8 * (total + 1)), sw.PinnedBuffer(2 * total)
+            h_o = h_o_buf.view(np.uint64)
+            h_o[:] = np.arange(total + 1, dtype=np.uint64) * np.uint64(L)
+            ta, tb = sw.BytesTape(h_a.array[: total * L], h_o, _keepalive=(h_a, h_o_buf)), sw.BytesTape(h_b.array[: total * L], h_o, _keepalive=(h_b, h_o_buf))
+            h_out = h_out_buf.view(np.uint16)
+            for _ in range(2):
+                lev.compute_pairs(multi, ta, tb, out=h_out)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                lev.compute_pairs(multi, ta, tb, out=h_out)
+            wall = (time.perf_counter() - t0) / 3 * 1e3
+            result["host_scope"] = {
+                "api": "swb_compute_pairs_view over swb_scope_create(0, %d): pinned host tapes sharded by bytes, chunked H2D on every GPU at once, u16 results" % world,
+                "gcups": cells / (wall * 1e-3) / 1e9, "ms_per_step": wall, "h2d_gbs_aggregate": (2.0 * total * L + 16.0 * total) / (wall * 1e-3) / 1e9,
+                "parity_ok": bool(np.array_equal(h_out.astype(np.uint64), want)), "parity_pairs_checked": total}
+            multi.close()
+        except Exception as exc:  # report, do not lose the rest of the line
+            result["single_process_error"] = f"{type(exc).__name__}: {exc}"
+    bench.barrier()
+    return result
+
+
+# ====================================================================================================== main
 
 def main():
     # The contract is ONE JSON line on stdout. Native libraries (NCCL prints its version banner on stdout) do not
@@ -127,6 +517,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (default: the workload's)")
     ap.add_argument("--algorithm", default="auto", choices=["auto", "wavefront", "bitparallel"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-gates", action="store_true", help="skip the gates (N = 1) / config4 (N > 1) blocks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -137,6 +528,7 @@ def main():
     n_pairs = args.pairs or default_pairs
     cells_per_pair = float(length * length)
     host_threads = os.cpu_count() or 1
+    config = shared_config(args.workload, config_name, n_pairs, length)
 
     from stringwars_b200 import datasets
 
@@ -144,24 +536,25 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        a, b = datasets.ascii_pairs(min(n_pairs, 1 << 18), length, seed=42)
+        sample_pairs = min(n_pairs, 1 << 18)
+        a, b = datasets.ascii_pairs(sample_pairs, length, seed=42)
         per_step = max(1.0, min(args.cpu_seconds, 120.0 / max(args.steps + args.warmup, 1)))
         for _ in range(args.warmup):
-            cpu_reference(a, b, cells_per_pair, per_step / 4, host_threads)
+            cpu_reference(a, b, cells_per_pair * sample_pairs, per_step / 4, host_threads)
         cells = secs = 0.0
         sample = 0
         for _ in range(args.steps):
-            g, sample, dt = cpu_reference(a, b, cells_per_pair, per_step, host_threads)
+            g, sample, dt = cpu_reference(a, b, cells_per_pair * sample_pairs, per_step, host_threads)
             cells += g * 1e9 * dt
             secs += dt
         value = cells / secs / 1e9
         line = {
             "impl": "reference", "metric": "GCUPS (DP cells/s) on batched Levenshtein", "value": value, "unit": "GCUPS",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 bit-vectors (CPU)", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {config_name}", "pairs_per_step": sample, "length": length},
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 bit-vectors (CPU)", "data": "synthetic (seed 42, iid printable ASCII)",
+            "config": config,
             "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": host_threads, "kind": "port",
-                             "sample": f"{sample} pair evaluations of {length}x{length} per step ({len(a)} distinct pairs repeated), rapidfuzz-class restatement (oracle/lev_oracle.c orc_rf_lev_bytes), {host_threads} threads"},
+                             "sample": f"{sample} pair evaluations of {length}x{length} per step ({len(a)} distinct pairs of the workload's generator, repeated), rapidfuzz-class restatement (oracle/lev_oracle.c orc_rf_lev_bytes), {host_threads} threads"},
             "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -177,6 +570,8 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    bench = Bench(torch, dist, device, world)
+    stream = bench.stream
 
     scope = sw.DeviceScope.gpu_device(local_rank)
     engine = sw.LevenshteinDistances(scope, 0, 1, 1, 1)
@@ -187,64 +582,24 @@ def main():
     for s in range(2):
         a, b = datasets.ascii_pairs(n_pairs, length, seed=42 + 1000 * rank + s, pinned=True)
         host_sets.append((a, b))
-        pad = lambda x: torch.cat([torch.from_numpy(x), torch.zeros(64, dtype=torch.uint8)]).to(device)
-        dev_sets.append((pad(a.data), torch.from_numpy(a.offsets.view(np.int64)).to(device),
-                         pad(b.data), torch.from_numpy(b.offsets.view(np.int64)).to(device)))
+        dev_sets.append((*to_device_tape(torch, a, device), *to_device_tape(torch, b, device)))
     d_out = torch.zeros(n_pairs, dtype=torch.int64, device=device)
     h_out = sw.PinnedBuffer(8 * n_pairs)
     h_out_arr = h_out.view(np.uint64)
     cells_step = cells_per_pair * n_pairs
     bytes_step_alg = 2.0 * length * n_pairs  # algorithmic bytes: len(a)+len(b) per pair
-    stream = torch.cuda.current_stream(device)
-
-    def device_step(i):
-        ad, ao, bd, bo = dev_sets[i & 1]
-        engine.compute_pairs_device(ad.data_ptr(), ao.data_ptr(), bd.data_ptr(), bo.data_ptr(), n_pairs, d_out.data_ptr(),
-                                    stream=stream.cuda_stream)
 
     def host_step(i):
         a, b = host_sets[i & 1]
         engine.compute_pairs(scope, a, b, out=h_out_arr)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(device)
-
-    def timed(step_fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for i in range(steps):
-            step_fn(i)
-        e1.record(stream)
-        torch.cuda.synchronize(device)
-        wall = time.perf_counter() - t0
-        barrier()
-        dev_ms = e0.elapsed_time(e1)
-        return dev_ms, wall * 1e3
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     # ---- device-resident value
-    for i in range(args.warmup):
-        device_step(i)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    if rank == 0:
         sampler.mark()
     launches0 = sw.launch_count()
-    engine.set_profiling(True)
-    dev_ms, wall_ms = timed(device_step, args.steps)
-    kernel_ms, kernel_launches = engine.kernel_time()
-    engine.set_profiling(False)
+    step_ms_local, kernel_ms, kernel_launches, kernel_name, device_step = resident_value(bench, engine, dev_sets, n_pairs, d_out, args.steps, args.warmup)
     launches = sw.launch_count() - launches0
     # The timed region is K x ~0.2 ms — shorter than one nvidia-smi poll. Keep the identical step running (untimed)
     # for ~0.4 s so the clock/throttle record covers the same work under sustained load.
@@ -254,70 +609,33 @@ def main():
         device_step(i_obs)
         i_obs += 1
     torch.cuda.synchronize(device)
-    kernel_name = engine.last_kernel
     # the device call synchronises once inside (schedule readback), so events and wall agree; report the larger
-    step_ms = max_over_ranks(max(dev_ms, wall_ms) / args.steps)
+    step_ms = bench.max_over_ranks(step_ms_local)
     value = cells_step * world / (step_ms * 1e-3) / 1e9
 
     # ---- e2e through the host C-ABI
     for i in range(args.warmup):
         host_step(i)
-    _, e2e_wall = timed(host_step, args.steps)
+    _, e2e_wall = bench.timed(host_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    e2e_ms = max_over_ranks(e2e_wall / args.steps)
+    e2e_ms = bench.max_over_ranks(e2e_wall / args.steps)
     e2e_value = cells_step * world / (e2e_ms * 1e-3) / 1e9
     checksum = int(h_out_arr.sum())
 
-    # ---- pair-load phase alone (HBM read rate of the staging loads)
-    engine.set_profiling(True)
-    for i in range(args.warmup + 5):
-        ad, ao, bd, bo = dev_sets[i & 1]
-        engine.load_phase_device(ad.data_ptr(), ao.data_ptr(), bd.data_ptr(), bo.data_ptr(), n_pairs, d_out.data_ptr(), stream=stream.cuda_stream)
-        if i == args.warmup - 1:
-            engine.kernel_time()
-    load_ms, load_n = engine.kernel_time()
-    engine.set_profiling(False)
-
-    # ---- N>1: the exchange the north_star names — ONE NCCL scatter of tape slices from rank 0, per-rank compute,
-    # ONE gather of results (stringwars_b200/dist.py). Whole batch (world x n_pairs) starts resident on rank 0.
-    scatter_gather = None
-    if world > 1:
-        from stringwars_b200 import dist as swdist
-        total_pairs = n_pairs * world
-        full_a = full_b = None
-        if rank == 0:
-            fa, fb = datasets.ascii_pairs(total_pairs, length, seed=4242)
-            full_a = (torch.from_numpy(fa.data.copy()).to(device), torch.from_numpy(fa.offsets.view(np.int64).copy()).to(device))
-            full_b = (torch.from_numpy(fb.data.copy()).to(device), torch.from_numpy(fb.offsets.view(np.int64).copy()).to(device))
-
-        def sg_compute(ad, ao, bd, bo):
-            n_local = ao.numel() - 1
-            res = torch.empty(n_local, dtype=torch.int64, device=device)
-            if ad.numel() == 0:
-                ad = torch.zeros(16, dtype=torch.uint8, device=device)
-            if bd.numel() == 0:
-                bd = torch.zeros(16, dtype=torch.uint8, device=device)
-            engine.compute_pairs_device(ad.data_ptr(), ao.data_ptr(), bd.data_ptr(), bo.data_ptr(), n_local, res.data_ptr(), stream=stream.cuda_stream)
-            return res
-
-        sg_checksum = None
-
-        def sg_step(i):
-            nonlocal sg_checksum
-            res = swdist.sharded_pairs(full_a, full_b, device, sg_compute, total_pairs)
-            if res is not None and sg_checksum is None:
-                sg_checksum = int(res.sum().item())
-
-        for i in range(2):
-            sg_step(i)
-        sg_steps = max(3, min(args.steps, 10))
-        sg_dev, sg_wall = timed(sg_step, sg_steps)
-        sg_ms = max_over_ranks(max(sg_dev, sg_wall) / sg_steps)
-        scatter_gather = {"value": cells_per_pair * total_pairs / (sg_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": sg_ms,
-                          "pairs": total_pairs, "what": "batch resident on rank 0 -> one grouped NCCL send/recv scatter -> per-rank kernels -> one grouped gather",
-                          "checksum": sg_checksum}
-
     peak, peak_src = measured_peaks()
+    load = load_phase(bench, engine, dev_sets, n_pairs, d_out, bytes_step_alg, peak)
+
+    extra = {}
+    if not args.no_gates:
+        if world == 1:
+            del dev_sets, d_out
+            torch.cuda.empty_cache()
+            extra["gates"] = run_gates(bench, sw, datasets, scope, engine, args, peak, host_threads)
+        else:
+            del dev_sets, d_out
+            torch.cuda.empty_cache()
+            extra["config4"] = run_config4(bench, sw, datasets, scope, engine, rank, local_rank, world, host_threads)
+
     traffic, traffic_src = None, None
     try:  # DRAM bytes per launch of this kernel on this workload, from the committed ncu --set full capture
         entry = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{kernel_name}|{args.workload}|{n_pairs}")
@@ -325,36 +643,32 @@ def main():
             traffic, traffic_src = entry["traffic"], entry["source"]
     except Exception:
         pass
-    achieved = bytes_step_alg / (kernel_ms / max(kernel_launches, 1) * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
-    load_gbs = bytes_step_alg / (load_ms / max(load_n, 1) * 1e-3) / 1e9 if load_ms > 0 else 0.0
+    achieved = bytes_step_alg / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
 
-    line = None
     if rank == 0:
         a0, b0 = host_sets[0]
-        cpu_gcups, cpu_sample, cpu_dt = (cpu_reference(a0, b0, cells_per_pair, args.cpu_seconds, host_threads) if world == 1 else (None, 0, 0))
+        cpu_gcups, cpu_sample, cpu_dt = (cpu_reference(a0, b0, cells_step, args.cpu_seconds, host_threads) if world == 1 else (None, 0, 0))
+        h2d_gbs = (bytes_step_alg + 16.0 * (n_pairs + 1)) / (e2e_ms * 1e-3) / 1e9
         line = {
             "metric": "GCUPS (DP cells/s) on batched Levenshtein", "value": value, "unit": "GCUPS", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32 bit-vectors" if "bitpar" in kernel_name else "int32",
+            "vs_baseline": None, "dtype": "u32 bit-vectors" if ("bitpar" in kernel_name or "short" in kernel_name) else "int32",
             "data": "synthetic (seed 42, iid printable ASCII)",
-            "config": {"workload": f"{args.workload}: {config_name}", "pairs_per_gpu": n_pairs, "length": length,
-                       "algorithm": args.algorithm, "kernel": kernel_name,
-                       "l2": "two input sets (2 x %.0f MB) rotated every step: larger than the 126 MB L2" % ((bytes_step_alg + 16.0 * n_pairs) / 1e6),
-                       "timing": "max(CUDA events on the launch stream, host wall) / steps, max over ranks"},
+            "config": config, "algorithm": args.algorithm, "kernel": kernel_name,
             "e2e": {"value": e2e_value, "unit": "GCUPS", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(bytes_step_alg + 2 * 8 * (n_pairs + 1)), "d2h_bytes_per_step": 8 * n_pairs,
-                    "api": "swb_compute_pairs (host tapes, pinned)"},
+                    "api": "swb_compute_pairs (host tapes, pinned)", "h2d_gbs": h2d_gbs,
+                    "bound": "PCIe: %d cells per input byte x the measured H2D rate; kernel-side the same batch runs at `value`" % int(cells_per_pair / (2 * length + 16))},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": kernel_name, "kernel_ms": kernel_ms / max(kernel_launches, 1), "peak_source": peak_src,
+                         "kernel": kernel_name, "kernel_ms": kernel_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_step_alg,
-                         "kernel_gcups": cells_step / (kernel_ms / max(kernel_launches, 1) * 1e-3) / 1e9 if kernel_ms else None,
-                         "load_phase": {"kernel": "load_phase_kernel", "achieved": load_gbs, "frac": load_gbs / peak, "ms": load_ms / max(load_n, 1)}},
+                         "kernel_gcups": cells_step / (kernel_ms * 1e-3) / 1e9 if kernel_ms else None,
+                         "load_phase": load},
             "clocks": dict(clocks or {}, note="nvidia-smi polled every 100 ms from the start of the timed region through an untimed 0.4 s continuation of the same step and the e2e region"),
             "checksum": checksum,
         }
-        if scatter_gather is not None:
-            line["scatter_gather"] = scatter_gather
+        line.update(extra)
         if cpu_gcups is not None:
             line["cpu_baseline"] = {"value": cpu_gcups, "unit": "GCUPS", "cores": host_threads, "kind": "port",
                                     "sample": f"{cpu_sample} pair evaluations of {length}x{length} in {cpu_dt:.1f} s ({len(a0)} distinct pairs repeated), rapidfuzz-class restatement (oracle/lev_oracle.c orc_rf_lev_bytes), {host_threads} threads"}

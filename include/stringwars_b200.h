@@ -214,6 +214,12 @@ SWB_API swb_status_t swb_compute_cross_view(swb_engine_t *engine, const swb_tape
                                             const swb_tape_view_t *candidates, void *out, size_t row_stride,
                                             swb_result_type_t out_type, const char **err);
 
+/* swb_compute_pairs_device (device memory of scope device `device_index`, enqueued on `cuda_stream`, no final
+ * synchronisation) over typed views and any result width. */
+SWB_API swb_status_t swb_compute_pairs_device_view(swb_engine_t *engine, int device_index, const swb_tape_view_t *a,
+                                                   const swb_tape_view_t *b, void *out, swb_result_type_t out_type,
+                                                   void *cuda_stream, const char **err);
+
 /* Resident tapes: upload once, compute many times — what `BytesTape<u64, UnifiedAlloc>` gives the reference after
  * the first touch (bench.rs:292-306; the timing loop at bench.rs:587-605 never copies). The tape is copied to
  * every device of the scope (a cross product needs all candidates everywhere; pairs are sharded by range).

@@ -37,6 +37,8 @@ SIGNATURES = {
     "swb_scope_create_devices": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), c_err]),
     "swb_compute_pairs_view": (ctypes.c_int, [ctypes.c_void_p, c_viewp, c_viewp, ctypes.c_void_p, ctypes.c_int, c_err]),
     "swb_compute_cross_view": (ctypes.c_int, [ctypes.c_void_p, c_viewp, c_viewp, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, c_err]),
+    "swb_compute_pairs_device_view": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_viewp, c_viewp, ctypes.c_void_p, ctypes.c_int,
+                                                     ctypes.c_void_p, c_err]),
     "swb_tape_upload": (ctypes.c_int, [ctypes.c_void_p, c_viewp, ctypes.POINTER(ctypes.c_void_p), c_err]),
     "swb_tape_destroy": (None, [ctypes.c_void_p]),
     "swb_tape_len": (ctypes.c_size_t, [ctypes.c_void_p]),

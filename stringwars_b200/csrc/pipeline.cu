@@ -292,6 +292,28 @@ extern "C" swb_status_t swb_compute_pairs_device(swb_engine_t *engine, int devic
     return run_device_batch(engine, device_index, ps, (cudaStream_t)cuda_stream, err);
 }
 
+extern "C" swb_status_t swb_compute_pairs_device_view(swb_engine_t *engine, int device_index, const swb_tape_view_t *a, const swb_tape_view_t *b,
+                                                      void *out, swb_result_type_t out_type, void *cuda_stream, const char **err) {
+    swb_status_t st = check_engine(engine, device_index, err);
+    if (st != SWB_OK) return st;
+    if (!a || !b) return fail(err, SWB_INVALID_ARG, "NULL view");
+    if (a->n != b->n) return fail(err, SWB_INVALID_ARG, "tapes differ in length: %zu vs %zu", a->n, b->n);
+    if (a->n == 0) return SWB_OK;
+    if (!a->data || !a->offsets || !b->data || !b->offsets || !out) return fail(err, SWB_INVALID_ARG, "NULL tape or output pointer");
+    if ((a->offset_bits != 64 && a->offset_bits != 32) || (b->offset_bits != 64 && b->offset_bits != 32)) return fail(err, SWB_INVALID_ARG, "offset_bits must be 64 or 32");
+    if (out_type != SWB_RESULT_64 && out_type != SWB_RESULT_32 && out_type != SWB_RESULT_16) return fail(err, SWB_INVALID_ARG, "unknown result type %d", (int)out_type);
+    SWB_CUDA(cudaSetDevice(engine->scope->devs[device_index].device));
+    const uint32_t offs32 = (a->offset_bits == 32 ? 1u : 0u) | (b->offset_bits == 32 ? 2u : 0u);
+    PairSpace ps = make_pair_space(a->data, a->offsets, b->data, b->offsets, a->n, 0, 0, out, (uint32_t)out_type, offs32);
+    if (engine->kind == ENGINE_LEVENSHTEIN_UTF8) {
+        uint64_t a_bytes = 0, b_bytes = 0;
+        if ((st = device_span(a->offsets, a->offset_bits / 8, a->n, (cudaStream_t)cuda_stream, &a_bytes, err)) != SWB_OK) return st;
+        if ((st = device_span(b->offsets, b->offset_bits / 8, b->n, (cudaStream_t)cuda_stream, &b_bytes, err)) != SWB_OK) return st;
+        return run_device_batch_utf8(engine, device_index, ps, a->n, b->n, a_bytes, b_bytes, (cudaStream_t)cuda_stream, err);
+    }
+    return run_device_batch(engine, device_index, ps, (cudaStream_t)cuda_stream, err);
+}
+
 extern "C" swb_status_t swb_compute_cross_device(swb_engine_t *engine, int device_index, const uint8_t *q_data,
                                                  const uint64_t *q_offsets, size_t n_queries, const uint8_t *c_data,
                                                  const uint64_t *c_offsets, size_t n_candidates, uint64_t *out,

@@ -268,6 +268,12 @@ class _Engine:
         _lib.check(_lib.lib().swb_compute_pairs_device(self._h, device_index, a_data, a_offsets, b_data, b_offsets,
                                                        n_pairs, out, stream, ctypes.byref(err)), err)
 
+    def compute_pairs_device_view(self, a_view: "_lib.TapeView", b_view: "_lib.TapeView", out: int, result_type: int = _lib.RESULT_64,
+                                  stream: int = 0, device_index: int = 0) -> None:
+        err = ctypes.c_char_p()
+        _lib.check(_lib.lib().swb_compute_pairs_device_view(self._h, device_index, ctypes.byref(a_view), ctypes.byref(b_view), out, result_type,
+                                                            stream, ctypes.byref(err)), err)
+
     def compute_cross_device(self, q_data: int, q_offsets: int, n_q: int, c_data: int, c_offsets: int, n_c: int,
                              out: int, row_stride: int, stream: int = 0, device_index: int = 0) -> None:
         err = ctypes.c_char_p()

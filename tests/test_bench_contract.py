@@ -28,11 +28,16 @@ def test_reference_arm_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]
+    # both arms describe the workload with the same `config` object
+    sys.path.insert(0, ROOT)
+    import bench
+    length, _, name = bench.WORKLOADS["ascii64"]
+    assert line["config"] == bench.shared_config("ascii64", name, 4096, length)
 
 
 @pytest.mark.gpu
 def test_our_arm_line():
-    line = _run(["--steps", "3", "--warmup", "3", "--cpu-seconds", "0.5", "--pairs", "131072"], 600)
+    line = _run(["--steps", "3", "--warmup", "3", "--cpu-seconds", "0.5", "--pairs", "131072", "--no-gates"], 600)
     assert BASE_KEYS | {"roofline", "clocks"} <= set(line)
     assert line["n_gpus"] == 1 and line["scaling"] == "weak" and line["vs_baseline"] is None
     assert line["gpu_launches"] >= line["steps"] and line["value"] > line["cpu_baseline"]["value"]

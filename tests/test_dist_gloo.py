@@ -20,7 +20,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n_pairs, ragged, result_path):
+def _worker(rank, world, port, n_pairs, ragged, result_path, chunks=None, narrow=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -36,7 +36,17 @@ def _worker(rank, world, port, n_pairs, ragged, result_path):
         out = orc.levenshtein_pairs(a_data.numpy(), a_offs.numpy().astype(np.uint64), b_data.numpy(), b_offs.numpy().astype(np.uint64))
         return torch.from_numpy(out.astype(np.int64))
 
-    got = swdist.sharded_pairs(a, b, device, compute, n_pairs)
+    if chunks is None and not narrow:
+        got = swdist.sharded_pairs(a, b, device, compute, n_pairs)
+    else:
+        # the chunked call shape: several chunks per shard, u32 offsets on received chunks, narrow results
+        def fill(a_data, a_offs, b_data, b_offs, out):
+            assert a_offs.dtype in (torch.int64, torch.int32)
+            out.copy_(compute(a_data, a_offs, b_data, b_offs).to(out.dtype))
+        stats = {}
+        got = swdist.scatter_compute_gather(a, b, device, fill, n_pairs, torch.int16 if narrow else torch.int64, chunks, stats=stats)
+        if rank == 0:
+            assert stats["chunks"] == (chunks or 1) and stats["sent_bytes"] >= 0
     if rank == 0:
         want = orc.levenshtein_pairs(ta.data, ta.offsets, tb.data, tb.offsets)
         ok = got is not None and np.array_equal(got.numpy().astype(np.uint64), want)
@@ -52,6 +62,25 @@ def test_scatter_compute_gather(tmp_path, world, n_pairs, ragged):
     result = tmp_path / "result.txt"
     mp.spawn(_worker, args=(world, _free_port(), n_pairs, ragged, str(result)), nprocs=world, join=True)
     assert result.read_text() == "ok"
+
+
+@pytest.mark.parametrize("world,n_pairs,ragged,chunks", [(2, 1001, True, 3), (3, 500, False, 4), (2, 5, True, 16), (3, 1, False, 2)])
+def test_chunked_scatter_narrow_results(tmp_path, world, n_pairs, ragged, chunks):
+    """C chunks per shard (more chunks than pairs included), int32 relative offsets, int16 results."""
+    result = tmp_path / "result.txt"
+    mp.spawn(_worker, args=(world, _free_port(), n_pairs, ragged, str(result), chunks, True), nprocs=world, join=True)
+    assert result.read_text() == "ok"
+
+
+def test_cut_table_is_monotonic_and_byte_balanced():
+    a, b = datasets.utf8_line_pairs(800, 30, 300, seed=4)
+    ao, bo = torch.from_numpy(a.offsets.astype(np.int64)), torch.from_numpy(b.offsets.astype(np.int64))
+    table = swdist.cut_table(ao, bo, 12).numpy()
+    cuts = table[0]
+    assert cuts[0] == 0 and cuts[-1] == 800 and (np.diff(cuts) >= 0).all()
+    assert np.array_equal(table[1], a.offsets[cuts].astype(np.int64)) and np.array_equal(table[2], b.offsets[cuts].astype(np.int64))
+    shares = np.diff(table[1] + table[2])
+    assert shares.max() - shares.min() <= 2 * 600
 
 
 def test_shard_bounds_balance_bytes():
