@@ -27,8 +27,8 @@ _i8p = ctypes.POINTER(ctypes.c_int8)
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "lev_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "lev_oracle.c"), os.path.join(_HERE, "align_bruteforce.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.run(["make", "-C", _HERE, "-B", "liblev_oracle.so"], check=True, capture_output=True)
     return _SO
 
@@ -48,6 +48,8 @@ def lib() -> ctypes.CDLL:
         L.orc_align_score.restype = ctypes.c_int64
         L.orc_align_score.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
                                       _u8p, _i8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.orc_align_bruteforce.restype = ctypes.c_int64
+        L.orc_align_bruteforce.argtypes = L.orc_align_score.argtypes
         L.orc_lev_pairs.restype = None
         L.orc_lev_pairs.argtypes = [ctypes.c_int, _u8p, _u64p, _u8p, _u64p, ctypes.c_size_t, _u64p, ctypes.c_int]
         L.orc_lev_pairs_timed.restype = ctypes.c_double
@@ -132,6 +134,16 @@ def align_score(a: bytes, b: bytes, byte_to_class, costs, open: int, extend: int
     cst = np.ascontiguousarray(costs, dtype=np.int8)
     return int(lib().orc_align_score(a, len(a), b, len(b), _p(btc, ctypes.c_uint8), _p(cst, ctypes.c_int8),
                                      open, extend, convention, int(local)))
+
+
+def align_bruteforce(a: bytes, b: bytes, byte_to_class, costs, open: int, extend: int,
+                     convention: int = GAP_STRINGZILLA, local: bool = False) -> int:
+    """Definition-level score: every alignment of two SHORT strings enumerated and scored (oracle/align_bruteforce.c).
+    Shares no code or recurrence with `align_score`."""
+    btc = np.ascontiguousarray(byte_to_class, dtype=np.uint8)
+    cst = np.ascontiguousarray(costs, dtype=np.int8)
+    return int(lib().orc_align_bruteforce(a, len(a), b, len(b), _p(btc, ctypes.c_uint8), _p(cst, ctypes.c_int8),
+                                          open, extend, convention, int(local)))
 
 
 def align_pairs(a_data, a_offs, b_data, b_offs, byte_to_class, costs, open: int, extend: int,

@@ -30,16 +30,17 @@ static swb_status_t launch_bitpar(swb_engine *eng, DeviceCtx &ctx, const PairSpa
 }
 
 // Patterns of at most 32 bytes with the pattern's match masks derived in registers (lev_short.cuh): no tables.
-template <int W>
+template <int W, bool LONG_PAT = false>
 static swb_status_t launch_short(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count,
                                  cudaStream_t stream, const char **err, uint32_t n_cap = 0xFFFFFFFFu) {
     const uint64_t blocks = (count + SHORT_THREADS - 1) / SHORT_THREADS;
     {
         ProfileBracket bracket(eng, ctx.device, stream);
-        lev_short_kernel<W><<<(unsigned)blocks, SHORT_THREADS, 0, stream>>>(ps, begin, count, n_cap);
+        lev_short_kernel<W, LONG_PAT><<<(unsigned)blocks, SHORT_THREADS, 0, stream>>>(ps, begin, count, n_cap);
     }
     g_launches++;
-    eng->last_kernel = W == 2 ? "lev_short<W=2>" : (W == 4 ? "lev_short<W=4>" : "lev_short<W=6>");
+    if (LONG_PAT) eng->last_kernel = W == 2 ? "lev_short<W=2,long>" : (W == 4 ? "lev_short<W=4,long>" : "lev_short<W=6,long>");
+    else eng->last_kernel = W == 2 ? "lev_short<W=2>" : (W == 4 ? "lev_short<W=4>" : "lev_short<W=6>");
     SWB_CUDA(cudaGetLastError());
     return SWB_OK;
 }
@@ -97,8 +98,11 @@ static swb_status_t launch_bitpar_cross(swb_engine *eng, DeviceCtx &ctx, const P
 
 swb_status_t launch_lev_bitpar(swb_engine *eng, DeviceCtx &ctx, int K, const PairSpace &ps, uint64_t begin, uint64_t count, uint32_t n_cap,
                                cudaStream_t stream, const char **err) {
-    // K <= 0 selects the register kernel of -K pattern words
+    // K < 0 selects the register kernel of -K pattern words (-K - 10: the longer string is the pattern)
     switch (K) {
+    case -12: return launch_short<2, true>(eng, ctx, ps, begin, count, stream, err, n_cap);
+    case -14: return launch_short<4, true>(eng, ctx, ps, begin, count, stream, err, n_cap);
+    case -16: return launch_short<6, true>(eng, ctx, ps, begin, count, stream, err, n_cap);
     case -2: return launch_short<2>(eng, ctx, ps, begin, count, stream, err, n_cap);
     case -4: return launch_short<4>(eng, ctx, ps, begin, count, stream, err, n_cap);
     case -6: return launch_short<6>(eng, ctx, ps, begin, count, stream, err, n_cap);
@@ -130,6 +134,9 @@ swb_status_t launch_lev_class(swb_engine *eng, DeviceCtx &ctx, const PairSpace &
     if ((exp_mask & 8) && max_m <= 32) return launch_bitpar<1>(eng, ctx, ps, begin, count, stream, err);
 #endif
     // register kernel up to 24 pattern bytes, thread-per-pair table kernels up to 256, lane-group kernels beyond
+    if (max_n <= 8) return launch_short<2, true>(eng, ctx, ps, begin, count, stream, err);
+    if (max_n <= 16) return launch_short<4, true>(eng, ctx, ps, begin, count, stream, err);
+    if (max_n <= SHORT_MAX_M) return launch_short<6, true>(eng, ctx, ps, begin, count, stream, err);
     if (max_m <= 8) return launch_short<2>(eng, ctx, ps, begin, count, stream, err);
     if (max_m <= 16) return launch_short<4>(eng, ctx, ps, begin, count, stream, err);
     if (max_m <= SHORT_MAX_M) return launch_short<6>(eng, ctx, ps, begin, count, stream, err);

@@ -86,24 +86,28 @@ __device__ __forceinline__ void short_columns(const uint32_t (&pat)[W], const ui
     }
 }
 
-// W = pattern words of the launch (the class's longest pattern): 2 (<= 8 bytes), 4 (<= 16), 6 (<= 24).
-template <int W>
+// W = pattern words of the launch: 2 (<= 8 bytes), 4 (<= 16), 6 (<= 24).
+// LONG_PAT picks which string of a pair is the pattern. false: the SHORTER one (any text length; W covers the class's
+// longest shorter string). true: the LONGER one, for batches whose every string fits the registers (W covers the longest
+// string of the batch — config 1's words): the columns are then the shorter string's symbols, and a column costs the same
+// whatever the pattern length, so a pair of lengths (la, lb) costs min(la, lb) column steps instead of max(la, lb).
+template <int W, bool LONG_PAT>
 __global__ void __launch_bounds__(SHORT_THREADS) lev_short_kernel(PairSpace ps, uint64_t begin, uint64_t count, uint32_t n_cap) {
     const uint64_t local = (uint64_t)blockIdx.x * SHORT_THREADS + threadIdx.x;
     if (local >= count) return;
     const uint32_t opaque0 = (uint32_t)(count >> 63); // run-time 0: see mad_lo in lev_bitpar.cuh
     const ShortConsts k{1u + opaque0, 2u + opaque0, 0x01010101u + opaque0, 256u + opaque0, 65536u + opaque0};
     const PairView pv = pair_at(ps, begin + local);
-    const bool swap = pv.la > pv.lb;
+    const bool swap = LONG_PAT ? pv.la < pv.lb : pv.la > pv.lb;
     const uint8_t *pat_p = swap ? pv.b : pv.a;
     const uint8_t *txt_p = swap ? pv.a : pv.b;
     const uint32_t m = swap ? pv.lb : pv.la;
     const uint32_t n = swap ? pv.la : pv.lb;
-    if (m == 0) {
-        store_result(ps, pv.out_index, n);
+    if (min(m, n) == 0) {
+        store_result(ps, pv.out_index, max(m, n));
         return;
     }
-    if (m > 4u * W || n > n_cap) return; // not this kernel's class, or a length the host has not validated yet (speculative launch)
+    if (m > 4u * W || max(m, n) > n_cap) return; // not this kernel's class, or a length the host has not validated yet (speculative launch)
 
     // pattern: up to two 16-byte pieces, re-aligned in registers to start at its first byte
     PieceStream pat_stream, txt_stream;

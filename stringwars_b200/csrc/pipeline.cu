@@ -137,7 +137,10 @@ static swb_status_t enqueue_scatter(DeviceCtx &ctx, PairSpace &ps, cudaStream_t 
 // The speculative kernel family of a uniform byte-Levenshtein batch: its launch geometry depends on nothing but the
 // pair count. Classes 0..3 are the table kernels of 1, 2, 4, 8 words; short patterns use the register kernels.
 static int spec_kernel_of(const Plan &plan) {
-    const uint32_t m = plan.max_m[0];
+    const uint32_t m = plan.max_m[0], n = plan.max_n[0];
+    if (n <= 8) return -12;
+    if (n <= 16) return -14;
+    if (n <= 24) return -16;
     if (m <= 8) return -2;
     if (m <= 16) return -4;
     if (m <= 24) return -6;

@@ -64,6 +64,11 @@ def chunks_for(total_bytes: int, world: int) -> int:
     return int(min(MAX_CHUNKS, max(1, total_bytes // max(world, 1) // TARGET_CHUNK_BYTES)))
 
 
+def _wire(t: torch.Tensor) -> torch.Tensor:
+    """What travels: the tensor's bytes (the NCCL process group has no int16, and a byte count is what a scatter is)."""
+    return t.view(torch.uint8) if t.dtype != torch.uint8 else t
+
+
 ComputeFn = Callable[[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor], None]
 
 
@@ -117,7 +122,7 @@ def scatter_compute_gather(a: Optional[Tuple[torch.Tensor, torch.Tensor]], b: Op
                           (a_offs[cut[k]: cut[k + 1] + 1] - a_at[k0]).to(torch.int32), (b_offs[cut[k]: cut[k + 1] + 1] - b_at[k0]).to(torch.int32)]
                 for t in pieces:
                     if t.numel():
-                        ops.append(dist.P2POp(dist.isend, t, r, group))
+                        ops.append(dist.P2POp(dist.isend, _wire(t), r, group))
                         sent += t.numel() * t.element_size()
                 keep.append(pieces)
             if ops:
@@ -130,7 +135,7 @@ def scatter_compute_gather(a: Optional[Tuple[torch.Tensor, torch.Tensor]], b: Op
         for r in range(world):
             rlo, rhi = cut[r * C], cut[(r + 1) * C]
             if r != src and rhi > rlo:
-                ops.append(dist.P2POp(dist.irecv, out[rlo:rhi], r, group))
+                ops.append(dist.P2POp(dist.irecv, _wire(out[rlo:rhi]), r, group))
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
@@ -154,7 +159,7 @@ def scatter_compute_gather(a: Optional[Tuple[torch.Tensor, torch.Tensor]], b: Op
         ao = torch.empty(cnt + 1, dtype=torch.int32, device=device)
         bo = torch.empty(cnt + 1, dtype=torch.int32, device=device)
         pieces = [a_buf[a_at[k] - a_at[k0]: a_at[k + 1] - a_at[k0]], b_buf[b_at[k] - b_at[k0]: b_at[k + 1] - b_at[k0]], ao, bo]
-        ops = [dist.P2POp(dist.irecv, t, src, group) for t in pieces if t.numel()]
+        ops = [dist.P2POp(dist.irecv, _wire(t), src, group) for t in pieces if t.numel()]
         chunk_reqs.append(dist.batch_isend_irecv(ops) if ops else [])
         chunk_offs.append((ao, bo))
     for c in range(C):
@@ -166,7 +171,7 @@ def scatter_compute_gather(a: Optional[Tuple[torch.Tensor, torch.Tensor]], b: Op
         ao, bo = chunk_offs[c]
         compute(a_buf, ao, b_buf, bo, local[cut[k] - lo: cut[k + 1] - lo])
     if hi > lo:
-        for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, local, src, group)]):
+        for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, _wire(local), src, group)]):
             req.wait()
     return None
 
