@@ -443,8 +443,12 @@ def run_config4(bench, sw, datasets, scope, engine, rank, local_rank, world, hos
                    "note": "scatter_gather_only = the same exchange with the kernels removed; the full step overlaps the two"}}
     last.clear()
 
-    # ---- the same exchange inside the C ABI: ONE process (rank 0) drives all N GPUs through `swb_scope_create(0, N)`
+    # ---- the same exchange inside the C ABI: ONE process (rank 0) drives all N GPUs through `swb_scope_create(0, N)`.
+    # The other ranks wait on a HOST barrier (gloo): an NCCL barrier would leave their all-reduce kernel spinning on the very
+    # GPUs rank 0 is about to use, and the time-slicing between the two processes' contexts would be what gets measured.
     bench.barrier()
+    torch.cuda.synchronize(device)
+    dist.barrier(group=bench.cpu_group)
     if rank == 0 and sw.device_count() >= world:
         try:
             multi = sw.DeviceScope.gpu_devices(0, world)
@@ -491,6 +495,7 @@ def run_config4(bench, sw, datasets, scope, engine, rank, local_rank, world, hos
             multi.close()
         except Exception as exc:  # report, do not lose the rest of the line
             result["single_process_error"] = f"{type(exc).__name__}: {exc}"
+    dist.barrier(group=bench.cpu_group)
     bench.barrier()
     return result
 
@@ -568,9 +573,14 @@ def main():
 
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    cpu_group = None
     if world > 1:
+        # NCCL's kernels on high-priority streams: a compute kernel that fills the machine must not hold a scatter chunk back
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=device)
+        cpu_group = dist.new_group(backend="gloo")  # host-side barrier: waiting ranks must not spin a kernel on their GPU
     bench = Bench(torch, dist, device, world)
+    bench.cpu_group = cpu_group
     stream = bench.stream
 
     scope = sw.DeviceScope.gpu_device(local_rank)

@@ -36,10 +36,15 @@ constexpr int NEG_BIG = -(1 << 28);
 // G lanes per pair, R rows per lane. LOCAL: Smith-Waterman. AFFINE: Gotoh E/F tracks. UNARY: match/mismatch
 // constants instead of the 32x32 table. SymT: uint8_t symbols, or uint32_t for decoded UTF-8 (codepoint-level
 // Levenshtein, bench.rs:437; compared raw, `cs.ident` must be set).
-template <int G, int R, bool LOCAL, bool AFFINE, bool UNARY, typename BoundT, typename SymT = uint8_t>
+// LONG: pairs too long for shared memory (the reference runs NW on multi-kilobyte XLSum lines,
+// similarities/README.md:19-23). Nothing is staged: a lane reads its R row symbols from global memory once per strip and one
+// column symbol per step (32 consecutive bytes per warp and step, L1-resident), and the boundary rows between strips live
+// in a global scratch row per pair (`bound_g`, `bound_stride` bytes apart) — the same recurrence with no length limit.
+template <int G, int R, bool LOCAL, bool AFFINE, bool UNARY, typename BoundT, typename SymT = uint8_t, bool LONG = false>
 __global__ void __launch_bounds__(WF_THREADS)
     align_wavefront_kernel(PairSpace ps, uint64_t begin, uint64_t count, AlignCosts cs, const AlignTables *__restrict__ tables,
-                           uint32_t slot_rows /* bytes reserved for the row string */, uint32_t slot_cols, uint32_t bound_cap) {
+                           uint32_t slot_rows /* bytes reserved for the row string */, uint32_t slot_cols, uint32_t bound_cap,
+                           uint8_t *bound_g, uint64_t bound_stride) {
     constexpr int PAIRS_PER_BLOCK = WF_THREADS / G;
     constexpr bool SHIFTED = !LOCAL && !AFFINE && UNARY; // cells hold H - gap*(i+j)
     extern __shared__ __align__(16) uint8_t smem[];
@@ -54,6 +59,7 @@ __global__ void __launch_bounds__(WF_THREADS)
     uint8_t *s_rows = my, *s_cols = my + slot_rows;
     BoundT *s_bh = reinterpret_cast<BoundT *>(my + slot_rows + slot_cols);
     BoundT *s_be = s_bh + bound_cap;
+    const SymT *rows_g = nullptr, *cols_g = nullptr;
 
     const bool need_tables = !cs.ident || !UNARY;
     if (need_tables)
@@ -72,17 +78,35 @@ __global__ void __launch_bounds__(WF_THREADS)
         m = swapped ? pv.lb : pv.la;
         n = swapped ? pv.la : pv.lb;
         out_index = pv.out_index;
-        mis_r = stage_string(s_rows, rows, m * (uint32_t)sizeof(SymT), lane, G);
-        mis_c = stage_string(s_cols, cols, n * (uint32_t)sizeof(SymT), lane, G);
+        if (LONG) {
+            rows_g = reinterpret_cast<const SymT *>(rows), cols_g = reinterpret_cast<const SymT *>(cols);
+            s_bh = reinterpret_cast<BoundT *>(bound_g + local * bound_stride);
+            s_be = s_bh + (n + 1u);
+        } else {
+            mis_r = stage_string(s_rows, rows, m * (uint32_t)sizeof(SymT), lane, G);
+            mis_c = stage_string(s_cols, cols, n * (uint32_t)sizeof(SymT), lane, G);
+        }
     }
     __syncthreads();
     SymT *rows_s = reinterpret_cast<SymT *>(s_rows + mis_r), *cols_s = reinterpret_cast<SymT *>(s_cols + mis_c);
     const int8_t *cost_tab = s_costs + (swapped ? 1024 : 0);
+    const bool map_classes = need_tables && sizeof(SymT) == 1;
     // Symbols -> classes, once, in place (the class map folds bytes into <= 32 classes, bench.rs:99-102).
-    if (need_tables && sizeof(SymT) == 1) {
+    if (map_classes && !LONG) {
         for (uint32_t i = lane; i < m; i += G) rows_s[i] = (SymT)s_class[(uint8_t)rows_s[i]];
         for (uint32_t j = lane; j < n; j += G) cols_s[j] = (SymT)s_class[(uint8_t)cols_s[j]];
     }
+    // one symbol of the row / column string as the cells compare it (LONG: straight from global memory, mapped on the way)
+    auto row_symbol = [&](uint32_t i) -> int {
+        if (!LONG) return (int)rows_s[i];
+        const SymT v = __ldg(rows_g + i);
+        return map_classes ? (int)s_class[(uint8_t)v] : (int)v;
+    };
+    auto col_symbol = [&](uint32_t j) -> int {
+        if (!LONG) return (int)cols_s[j];
+        const SymT v = __ldg(cols_g + j);
+        return map_classes ? (int)s_class[(uint8_t)v] : (int)v;
+    };
 
     // Warp-uniform trip counts (groups of a warp may hold pairs of different sizes).
     uint32_t n_max = n, m_max = m;
@@ -101,7 +125,7 @@ __global__ void __launch_bounds__(WF_THREADS)
     const int c_mismatch = SHIFTED ? cs.mismatch - 2 * gap : cs.mismatch;
     // The boundary row lives in shared memory only when it is not identically computable: shifted cells have
     // an all-zero top row, so a single strip never touches it.
-    const bool use_bound = !SHIFTED || strips > 1;
+    const bool use_bound = !SHIFTED || strips > 1 || LONG;
     if (use_bound) {
         for (uint32_t j = lane; j <= n && have; j += G) {
             const int h = (LOCAL || SHIFTED) ? 0 : (j == 0 ? 0 : cs.first + (int)(j - 1) * cs.next);
@@ -125,7 +149,7 @@ __global__ void __launch_bounds__(WF_THREADS)
         for (int r = 0; r < R; ++r) {
             const uint32_t i = row0 + r; // 0-based row
             const bool ok = strip_live && i < m;
-            rc[r] = ok ? (int)rows_s[i] : -1; // -1 is no byte, no class and no packed UTF-8 symbol
+            rc[r] = ok ? row_symbol(i) : -1; // -1 is no byte, no class and no packed UTF-8 symbol
             if (ok) valid_mask |= 1u << r;
             HA[r] = HB[r] = (LOCAL || SHIFTED) ? 0 : cs.first + (int)i * cs.next; // H[i+1][0]
             Fl[r] = e_floor;
@@ -138,7 +162,7 @@ __global__ void __launch_bounds__(WF_THREADS)
         // One skewed step: reads Hold (column j-1), writes Hnew (column j). GUARDED=false is the steady state in
         // which every lane of the warp is inside its matrix: no predicate, no branch, no register copies.
         auto cells = [&](const int(&Hold)[R], int(&Hnew)[R], uint32_t j0, int recv_h, int recv_e) {
-            const int cc = (int)cols_s[j0];
+            const int cc = col_symbol(j0);
             int up_h = recv_h, up_e = recv_e;
             if (lane == 0) {
                 up_h = use_bound ? (int)s_bh[j0 + 1] : 0;

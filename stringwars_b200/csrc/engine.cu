@@ -140,13 +140,15 @@ extern "C" swb_status_t swb_scope_create_devices(const int *devices, int num_dev
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c.compute_stream, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) {
             // highest priority: the (tiny) schedule kernel must get SM slots while a compute kernel launched just
-            // before it on another stream still has blocks waiting, otherwise it only runs in that kernel's tail
+            // before it on another stream still has blocks waiting, otherwise it only runs in that kernel's tail. Same for
+            // the NCCL kernels of the scatter: a compute kernel that fills the machine would otherwise hold every later
+            // chunk's send back until its own tail (measured: the exchange then serialises behind the root's shard).
             int least = 0, greatest = 0;
             cudaDeviceGetStreamPriorityRange(&least, &greatest);
             e = cudaStreamCreateWithPriority(&c.side_stream, cudaStreamNonBlocking, greatest);
+            if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c.comm_stream, cudaStreamNonBlocking, greatest);
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c.ev_inputs, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreate(&c.ev_t0);

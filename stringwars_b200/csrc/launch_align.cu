@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "align_wavefront.cuh"
 
@@ -21,15 +22,34 @@ static swb_status_t launch_wavefront_t(swb_engine *eng, DeviceCtx &ctx, int dev_
     const uint32_t bound_cap = (SHIFTED && single_strip) ? 0u : max_n + 1u; // shifted single-strip cells need no boundary row
     const uint32_t bound_bytes = round16(bound_cap * (uint32_t)sizeof(BoundT) * (AFFINE ? 2u : 1u));
     const size_t smem = 2304 + (size_t)PPB * (slot_rows + slot_cols + bound_bytes);
-    if (smem > (size_t)ctx.max_smem_optin)
+    if (smem > (size_t)ctx.max_smem_optin) {
+        if constexpr (G == 32 && std::is_same<BoundT, int32_t>::value) {
+            // Too long to stage: the LONG variant streams both strings from global memory and parks the boundary rows in
+            // a global scratch row per pair; sub-batches keep that scratch under 1 GiB whatever the class holds.
+            auto long_kernel = align_wavefront_kernel<G, R, LOCAL, AFFINE, UNARY, BoundT, SymT, true>;
+            const uint64_t stride = (((uint64_t)max_n + 1u) * sizeof(BoundT) * (AFFINE ? 2u : 1u) + 15u) & ~(uint64_t)15u;
+            const uint64_t per_launch = std::max<uint64_t>(PPB, std::min<uint64_t>(count, (1ull << 30) / stride) / PPB * PPB);
+            SWB_CUDA(ctx.hscratch.reserve(std::min<uint64_t>(count, per_launch) * stride));
+            for (uint64_t done = 0; done < count; done += per_launch) {
+                const uint64_t now = std::min<uint64_t>(per_launch, count - done);
+                ProfileBracket bracket(eng, ctx.device, stream);
+                long_kernel<<<(unsigned)((now + PPB - 1) / PPB), WF_THREADS, 2304, stream>>>(ps, begin + done, now, cs, eng->d_tables[dev_index], 0u, 0u, 0u,
+                                                                                         (uint8_t *)ctx.hscratch.ptr, stride);
+                g_launches++;
+                SWB_CUDA(cudaGetLastError());
+            }
+            eng->last_kernel = "align_wavefront<G=32,R=16,long>";
+            return SWB_OK;
+        }
         return fail(err, SWB_TOO_LONG, "pair of %u x %u bytes needs %zu B of shared memory per block (limit %d)", max_m, max_n,
                     smem, ctx.max_smem_optin);
+    }
     auto kernel = align_wavefront_kernel<G, R, LOCAL, AFFINE, UNARY, BoundT, SymT>;
     SWB_CUDA(allow_smem((const void *)kernel, ctx.device, smem));
     const uint64_t blocks = (count + PPB - 1) / PPB;
     {
         ProfileBracket bracket(eng, ctx.device, stream);
-        kernel<<<(unsigned)blocks, WF_THREADS, smem, stream>>>(ps, begin, count, cs, eng->d_tables[dev_index], slot_rows, slot_cols, bound_cap);
+        kernel<<<(unsigned)blocks, WF_THREADS, smem, stream>>>(ps, begin, count, cs, eng->d_tables[dev_index], slot_rows, slot_cols, bound_cap, nullptr, 0ull);
     }
     g_launches++;
     SWB_CUDA(cudaGetLastError());
@@ -98,6 +118,8 @@ swb_status_t launch_wavefront(swb_engine *eng, DeviceCtx &ctx, int dev_index, co
     SWB_GR(16, 16, "align_wavefront<G=16,R=16>")
     SWB_GR(32, 16, "align_wavefront<G=32,R=16>")
 #undef SWB_GR
+    if (st == SWB_TOO_LONG && narrow) // int16 boundary rows have no global-memory variant: the int32 one does
+        st = launch_wavefront_gr<32, 16>(eng, ctx, dev_index, ps, begin, count, cs, local, affine, eng->unary, false, max_m, max_n, stream, err);
     return st;
 }
 

@@ -321,3 +321,39 @@ def test_large_gap_costs_on_tiny_strings(scope, oracle):
                 eng = cls(scope, btc, costs, open_, extend).set_gap_convention(conv)
                 want = oracle.align_pairs(a.data, a.offsets, b.data, b.offsets, btc, costs, open_, extend, convention=conv, local=local)
                 assert np.array_equal(eng.compute_pairs(scope, a, b), want), (open_, extend, local, conv, eng.last_kernel)
+
+
+# ------------------------------------------------------------------------------------------ long alignments
+
+def test_alignments_longer_than_shared_memory(scope, oracle):
+    """NW / SW (linear, affine, general table) and the code-point engine on pairs far beyond what a block can stage
+    (~10 KB strings used to fail with SWB_TOO_LONG): the global-memory variant of the wavefront kernel,
+    mixed in one batch with short pairs, bit-exact with the oracle."""
+    rng = np.random.default_rng(77)
+    lens_a = [30_000, 12_345, 50, 21_000, 1]
+    lens_b = [28_500, 40_000, 60, 9, 16_000]
+    alphabet = np.frombuffer(b"ACGT", dtype=np.uint8)
+    a = datasets._ragged(np.array(lens_a), alphabet, rng, False)
+    b = datasets._ragged(np.array(lens_b), alphabet, rng, False)
+    # make pair 0 near-identical so that long runs of matches and real gaps both occur
+    b.data[: 20_000] = a.data[: 20_000]
+    btc, costs = sw.unary_class_costs(2, -1)
+    rng2 = np.random.default_rng(5)
+    table = rng2.integers(-4, 5, size=(32, 32)).astype(np.int8)
+    for cls, local in ((sw.NeedlemanWunschScores, False), (sw.SmithWatermanScores, True)):
+        for (bt, cs), (op, ex) in (((btc, costs), (-2, -2)), ((btc, costs), (-5, -1)), ((btc, table), (-3, -1))):
+            eng = cls(scope, bt, cs, op, ex)
+            got = eng.compute_pairs(scope, a, b)
+            want = oracle.align_pairs(a.data, a.offsets, b.data, b.offsets, bt, cs, op, ex, local=local, threads=8)
+            assert np.array_equal(got, want), (cls.__name__, op, ex, got, want, eng.last_kernel)
+    # byte Levenshtein through the wavefront family and the code-point engine on long multi-byte text
+    lev = sw.LevenshteinDistances(scope).set_algorithm(sw.ALGO_WAVEFRONT)
+    want = oracle.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, oracle.RAPIDFUZZ_CLASS, threads=8)
+    assert np.array_equal(lev.compute_pairs(scope, a, b), want)
+    words = ["жук", "naïve", "日本語", "x", "ß", "Ω"]
+    long_a = " ".join(words[int(i)] for i in rng.integers(0, len(words), size=9000))
+    long_b = " ".join(words[int(i)] for i in rng.integers(0, len(words), size=8000))
+    ua, ub = BytesTape.from_strings([long_a, "короткая", long_a[:3000]]), BytesTape.from_strings([long_b, long_b[:5000], long_a[:2990] + "Ж"])
+    utf8 = sw.LevenshteinDistancesUtf8(scope)
+    want = oracle.levenshtein_pairs(ua.data, ua.offsets, ub.data, ub.offsets, oracle.UTF8, threads=8)
+    assert np.array_equal(utf8.compute_pairs(scope, ua, ub), want), utf8.last_kernel
