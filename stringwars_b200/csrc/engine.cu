@@ -87,7 +87,7 @@ static void destroy_ctx(DeviceCtx &c) {
     if (c.ev_offsets) cudaEventDestroy(c.ev_offsets);
     for (auto e : c.ev_chunks) cudaEventDestroy(e);
     for (DeviceBuffer *b : {&c.order, &c.a_data, &c.a_offs, &c.b_data, &c.b_offs, &c.out, &c.sym_a, &c.sym_a_offs, &c.sym_b, &c.sym_b_offs,
-                            &c.scan_tmp, &c.flags, &c.hscratch, &c.rx_a, &c.rx_b, &c.rx_a_offs, &c.rx_b_offs, &c.rx_out})
+                            &c.scan_tmp, &c.flags, &c.hscratch, &c.ren_a, &c.ren_a_offs, &c.ren_b, &c.ren_b_offs, &c.rx_a, &c.rx_b, &c.rx_a_offs, &c.rx_b_offs, &c.rx_out})
         b->release();
 }
 

@@ -91,6 +91,7 @@ struct DeviceCtx {
     std::vector<cudaEvent_t> ev_chunks;
     DeviceBuffer order, a_data, a_offs, b_data, b_offs, out;
     DeviceBuffer sym_a, sym_a_offs, sym_b, sym_b_offs, scan_tmp, flags; // UTF-8 engine scratch
+    DeviceBuffer ren_a, ren_a_offs, ren_b, ren_b_offs;                   // UTF-8 engine: pairs renamed to byte alphabets
     DeviceBuffer hscratch; // per-column delta bits / boundary rows between row strips of the long-string kernels
     // multi_gpu.cu: receive buffers of a scattered shard, streams / events of the NCCL exchange
     DeviceBuffer rx_a, rx_b, rx_a_offs, rx_b_offs, rx_out;

@@ -254,6 +254,31 @@ swb_status_t swb::run_device_batch_utf8(swb_engine *eng, int dev_index, PairSpac
     sym.b_data = same_tape ? sym.a_data : (const uint8_t *)ctx.sym_b.ptr;
     sym.b_offs = same_tape ? sym.a_offs : (const uint64_t *)ctx.sym_b_offs.ptr;
     sym.len_shift = 2, sym.offs32 = 0;
+    // Element-wise pairs: rename every pair's symbols to a byte alphabet (utf8_remap_kernel) and run the byte kernels. A
+    // pair with more than 255 distinct symbols in its shorter string keeps the whole batch on the 32-bit wavefront kernel.
+    if (ps.n_c == 0 && eng->algorithm != SWB_ALGO_WAVEFRONT) {
+        SWB_CUDA(ctx.ren_a.reserve(a_bytes + 64));
+        SWB_CUDA(ctx.ren_b.reserve(b_bytes + 64));
+        SWB_CUDA(ctx.ren_a_offs.reserve((n_a + 1) * sizeof(uint64_t)));
+        SWB_CUDA(ctx.ren_b_offs.reserve((n_b + 1) * sizeof(uint64_t)));
+        SWB_CUDA(cudaMemsetAsync(d_flag + 1, 0, sizeof(uint32_t), stream));
+        const unsigned blocks = (unsigned)((ps.n_pairs + REMAP_WARPS - 1) / REMAP_WARPS);
+        utf8_remap_kernel<<<blocks, 32 * REMAP_WARPS, 0, stream>>>((const uint32_t *)sym.a_data, sym.a_offs, (const uint32_t *)sym.b_data, sym.b_offs, ps.n_pairs,
+                                                                  (uint8_t *)ctx.ren_a.ptr, (uint8_t *)ctx.ren_b.ptr, (uint64_t *)ctx.ren_a_offs.ptr,
+                                                                  (uint64_t *)ctx.ren_b_offs.ptr, d_flag + 1);
+        g_launches++;
+        SWB_CUDA(cudaGetLastError());
+        uint32_t h_overflow = 0;
+        SWB_CUDA(cudaMemcpyAsync(&h_overflow, d_flag + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        SWB_CUDA(cudaStreamSynchronize(stream));
+        if (h_overflow == 0) {
+            PairSpace ren = ps;
+            ren.a_data = (const uint8_t *)ctx.ren_a.ptr, ren.a_offs = (const uint64_t *)ctx.ren_a_offs.ptr;
+            ren.b_data = (const uint8_t *)ctx.ren_b.ptr, ren.b_offs = (const uint64_t *)ctx.ren_b_offs.ptr;
+            ren.len_shift = 0, ren.offs32 = 0;
+            return run_device_batch(eng, dev_index, ren, stream, err);
+        }
+    }
     return run_device_batch(eng, dev_index, sym, stream, err);
 }
 

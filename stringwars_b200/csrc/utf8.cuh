@@ -67,4 +67,85 @@ __global__ void __launch_bounds__(256) utf8_pack_kernel(const uint8_t *data, con
     }
 }
 
+// Per-pair alphabet compaction: the bit-vector kernels index their match tables by BYTE, and an edit distance only ever
+// asks whether pattern symbol i equals text symbol j. So each pair's 32-bit symbols are renamed to bytes: the distinct
+// symbols of the pair's SHORTER string get ids 1, 2, ... in hash-table order, the other string is translated through the
+// same dictionary and everything it holds that the shorter string does not becomes 0 (which equals no id). The renamed
+// pair has exactly the distance of the original, and runs on the byte kernels (16+ TCUPS instead of the 32-bit
+// wavefront's 2). One warp per pair; the dictionary is an open-addressing table of REMAP_SLOTS keys in shared memory.
+// A pair whose shorter string has more than 255 distinct symbols raises `overflow` (the host then keeps the batch on the
+// 32-bit wavefront kernel).
+constexpr int REMAP_SLOTS = 512;
+constexpr int REMAP_WARPS = 4;
+constexpr uint32_t REMAP_EMPTY = 0xFFFFFFFFu; // no packed UTF-8 symbol: continuation bytes are never 0xFF
+
+__device__ __forceinline__ uint32_t remap_hash(uint32_t key) { return (key * 0x9E3779B1u) >> (32 - 9); }
+
+__global__ void __launch_bounds__(32 * REMAP_WARPS)
+    utf8_remap_kernel(const uint32_t *a_sym, const uint64_t *a_so, const uint32_t *b_sym, const uint64_t *b_so, uint64_t n_pairs, uint8_t *a_out,
+                      uint8_t *b_out, uint64_t *a_oo, uint64_t *b_oo, uint32_t *overflow) {
+    __shared__ uint32_t s_keys[REMAP_WARPS][REMAP_SLOTS];
+    __shared__ uint8_t s_ids[REMAP_WARPS][REMAP_SLOTS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t pair = (uint64_t)blockIdx.x * REMAP_WARPS + warp;
+    if (pair >= n_pairs) return;
+    uint32_t *keys = s_keys[warp];
+    uint8_t *ids = s_ids[warp];
+    const uint64_t a0 = a_so[pair] >> 2, a1 = a_so[pair + 1] >> 2, b0 = b_so[pair] >> 2, b1 = b_so[pair + 1] >> 2;
+    const uint32_t la = (uint32_t)(a1 - a0), lb = (uint32_t)(b1 - b0);
+    if (lane == 0) {
+        a_oo[pair] = a0, b_oo[pair] = b0;
+        if (pair + 1 == n_pairs) a_oo[n_pairs] = a1, b_oo[n_pairs] = b1;
+    }
+    const bool dict_is_a = la <= lb;
+    const uint32_t *dict = dict_is_a ? a_sym + a0 : b_sym + b0;
+    const uint32_t dict_len = dict_is_a ? la : lb;
+    for (int i = lane; i < REMAP_SLOTS; i += 32) keys[i] = REMAP_EMPTY;
+    __syncwarp();
+    bool failed = false;
+    for (uint32_t k = lane; k < dict_len; k += 32) {
+        const uint32_t key = dict[k];
+        uint32_t h = remap_hash(key);
+        int probes = 0;
+        for (; probes < REMAP_SLOTS; ++probes, h = (h + 1u) & (REMAP_SLOTS - 1)) {
+            const uint32_t prev = atomicCAS(&keys[h], REMAP_EMPTY, key);
+            if (prev == REMAP_EMPTY || prev == key) break;
+        }
+        failed |= probes == REMAP_SLOTS;
+    }
+    __syncwarp();
+    // ids in slot order: 1 + number of occupied slots before this one
+    uint32_t distinct = 0;
+    for (int r = 0; r < REMAP_SLOTS / 32; ++r) {
+        const bool occupied = keys[r * 32 + lane] != REMAP_EMPTY;
+        const uint32_t mask = __ballot_sync(0xffffffffu, occupied);
+        const uint32_t id = distinct + __popc(mask & ((1u << lane) - 1u)) + 1u;
+        ids[r * 32 + lane] = (uint8_t)id;
+        distinct += __popc(mask);
+    }
+    __syncwarp();
+    if (__any_sync(0xffffffffu, failed) || distinct > 255u) {
+        if (lane == 0) atomicOr(overflow, 1u);
+        return;
+    }
+    auto translate = [&](const uint32_t *sym, uint32_t len, uint8_t *out) {
+        for (uint32_t k = lane; k < len; k += 32) {
+            const uint32_t key = sym[k];
+            uint32_t h = remap_hash(key);
+            uint32_t id = 0;
+            for (int probes = 0; probes < REMAP_SLOTS; ++probes, h = (h + 1u) & (REMAP_SLOTS - 1)) {
+                const uint32_t at = keys[h];
+                if (at == key) {
+                    id = ids[h];
+                    break;
+                }
+                if (at == REMAP_EMPTY) break;
+            }
+            out[k] = (uint8_t)id;
+        }
+    };
+    translate(a_sym + a0, la, a_out + a0);
+    translate(b_sym + b0, lb, b_out + b0);
+}
+
 } // namespace swb

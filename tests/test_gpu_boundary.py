@@ -357,3 +357,33 @@ def test_alignments_longer_than_shared_memory(scope, oracle):
     utf8 = sw.LevenshteinDistancesUtf8(scope)
     want = oracle.levenshtein_pairs(ua.data, ua.offsets, ub.data, ub.offsets, oracle.UTF8, threads=8)
     assert np.array_equal(utf8.compute_pairs(scope, ua, ub), want), utf8.last_kernel
+
+
+def test_codepoint_engine_alphabet_compaction_and_its_fallback(scope, oracle):
+    """Pairs whose symbols are renamed to bytes run the bit-vector kernels; a pair whose shorter string holds more than
+    255 distinct code points keeps its batch on the 32-bit wavefront kernel. Both bit-exact with the oracle."""
+    rng = np.random.default_rng(99)
+    utf8 = sw.LevenshteinDistancesUtf8(scope)
+    a, b = datasets.utf8_line_pairs(3000, seed=8)
+    want = oracle.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, oracle.UTF8, threads=8)
+    assert np.array_equal(utf8.compute_pairs(scope, a, b), want)
+    assert "bitpar" in utf8.last_kernel or "short" in utf8.last_kernel, utf8.last_kernel
+    # symbols shared and not shared between the two strings, 2/3/4-byte code points, repeated symbols, empties
+    pool = [chr(c) for c in list(range(0x430, 0x460)) + list(range(0x4E00, 0x4E40)) + list(range(0x1F600, 0x1F620)) + list(range(0x61, 0x7B))]
+    sa = ["".join(pool[int(i)] for i in rng.integers(0, len(pool), size=int(rng.integers(0, 90)))) for _ in range(4000)]
+    sb = ["".join(pool[int(i)] for i in rng.integers(0, len(pool), size=int(rng.integers(0, 90)))) for _ in range(4000)]
+    for i in range(0, 4000, 3):  # near-identical pairs
+        chars = list(sa[i])
+        if chars:
+            chars[int(rng.integers(0, len(chars)))] = pool[int(rng.integers(0, len(pool)))]
+        sb[i] = "".join(chars)
+    ta, tb = BytesTape.from_strings(sa), BytesTape.from_strings(sb)
+    want = oracle.levenshtein_pairs(ta.data, ta.offsets, tb.data, tb.offsets, oracle.UTF8, threads=8)
+    assert np.array_equal(utf8.compute_pairs(scope, ta, tb), want), utf8.last_kernel
+    # more than 255 distinct code points in the shorter string of ONE pair: whole batch falls back, still exact
+    wide = "".join(chr(0x4E00 + i) for i in range(300))
+    sa2, sb2 = sa[:50] + [wide], sb[:50] + [wide[::-1] + "ж"]
+    ta, tb = BytesTape.from_strings(sa2), BytesTape.from_strings(sb2)
+    want = oracle.levenshtein_pairs(ta.data, ta.offsets, tb.data, tb.offsets, oracle.UTF8, threads=8)
+    assert np.array_equal(utf8.compute_pairs(scope, ta, tb), want)
+    assert "wavefront" in utf8.last_kernel, utf8.last_kernel
