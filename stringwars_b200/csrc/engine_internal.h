@@ -138,6 +138,7 @@ struct swb_engine {
     swb::AlignTables tables;
     std::vector<swb::AlignTables *> d_tables; // per device
     const char *last_kernel = "none";
+    uint32_t spec_cross_q = 0, spec_cross_n = 0; // cross products: longest query / candidate of the last call that took the cross kernel (0: do not speculate)
     uint32_t spec_max_n = 0; // longest text of that batch: the speculative kernel skips anything longer (unvalidated lengths)
     int spec_class = 0; // kernel code (launch_lev_bitpar's K) of the last uniform batch on the device-resident path; 0: do not speculate
     bool profiling = false;
@@ -208,7 +209,7 @@ swb_status_t launch_lev_bitpar(swb_engine *eng, DeviceCtx &ctx, int K, const Pai
                                cudaStream_t stream, const char **err);
 // cross product with per-query table reuse; max_q <= 256
 swb_status_t launch_lev_cross(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint32_t n_queries, uint32_t cands_per_block,
-                              uint32_t max_q, cudaStream_t stream, const char **err);
+                              uint32_t max_q, uint32_t n_cap, cudaStream_t stream, const char **err);
 
 // launch_align.cu / launch_packed.cu: wavefront kernels (Levenshtein in wavefront mode, UTF-8 symbols, NW, SW).
 swb_status_t launch_wavefront(swb_engine *eng, DeviceCtx &ctx, int dev_index, const PairSpace &ps, uint64_t begin, uint64_t count,

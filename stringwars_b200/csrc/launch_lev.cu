@@ -80,7 +80,7 @@ static swb_status_t launch_bitpar_coop(swb_engine *eng, DeviceCtx &ctx, const Pa
 // Cross product with table reuse: one thread per query, candidates swept (lev_bitpar_cross.cuh).
 template <int K>
 static swb_status_t launch_bitpar_cross(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint32_t n_queries, uint32_t cands_per_block,
-                                        const char *name, cudaStream_t stream, const char **err) {
+                                        const char *name, uint32_t n_cap, cudaStream_t stream, const char **err) {
     constexpr int T = CrossConfig<K>::THREADS;
     const uint32_t chunk = 1024;
     const size_t smem = (size_t)32 * T * K * 4 + (((size_t)T * (CROSS_TILE + 1) * 4 + 15) & ~(size_t)15) + chunk + 32;
@@ -88,7 +88,7 @@ static swb_status_t launch_bitpar_cross(swb_engine *eng, DeviceCtx &ctx, const P
     const dim3 grid((n_queries + T - 1) / T, (unsigned)((ps.n_c + cands_per_block - 1) / cands_per_block));
     {
         ProfileBracket bracket(eng, ctx.device, stream);
-        lev_bitpar_cross_kernel<K><<<grid, T, smem, stream>>>(ps, n_queries, cands_per_block, chunk);
+        lev_bitpar_cross_kernel<K><<<grid, T, smem, stream>>>(ps, n_queries, cands_per_block, chunk, n_cap);
     }
     g_launches++;
     eng->last_kernel = name;
@@ -115,11 +115,11 @@ swb_status_t launch_lev_bitpar(swb_engine *eng, DeviceCtx &ctx, int K, const Pai
 }
 
 swb_status_t launch_lev_cross(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint32_t n_queries, uint32_t cands_per_block,
-                              uint32_t max_q, cudaStream_t stream, const char **err) {
-    if (max_q <= 32) return launch_bitpar_cross<1>(eng, ctx, ps, n_queries, cands_per_block, "lev_bitpar_cross<K=1>", stream, err);
-    if (max_q <= 64) return launch_bitpar_cross<2>(eng, ctx, ps, n_queries, cands_per_block, "lev_bitpar_cross<K=2>", stream, err);
-    if (max_q <= 128) return launch_bitpar_cross<4>(eng, ctx, ps, n_queries, cands_per_block, "lev_bitpar_cross<K=4>", stream, err);
-    return launch_bitpar_cross<8>(eng, ctx, ps, n_queries, cands_per_block, "lev_bitpar_cross<K=8>", stream, err);
+                              uint32_t max_q, uint32_t n_cap, cudaStream_t stream, const char **err) {
+    if (max_q <= 32) return launch_bitpar_cross<1>(eng, ctx, ps, n_queries, cands_per_block, "lev_bitpar_cross<K=1>", n_cap, stream, err);
+    if (max_q <= 64) return launch_bitpar_cross<2>(eng, ctx, ps, n_queries, cands_per_block, "lev_bitpar_cross<K=2>", n_cap, stream, err);
+    if (max_q <= 128) return launch_bitpar_cross<4>(eng, ctx, ps, n_queries, cands_per_block, "lev_bitpar_cross<K=4>", n_cap, stream, err);
+    return launch_bitpar_cross<8>(eng, ctx, ps, n_queries, cands_per_block, "lev_bitpar_cross<K=8>", n_cap, stream, err);
 }
 
 swb_status_t launch_lev_class(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count, uint32_t max_m,

@@ -26,7 +26,7 @@ constexpr int CROSS_TILE = 16; // candidates per result tile: 16 x u64 = one 128
 
 template <int K>
 __global__ void __launch_bounds__(CrossConfig<K>::THREADS)
-    lev_bitpar_cross_kernel(PairSpace ps, uint32_t n_queries, uint32_t cands_per_block, uint32_t chunk) {
+    lev_bitpar_cross_kernel(PairSpace ps, uint32_t n_queries, uint32_t cands_per_block, uint32_t chunk, uint32_t n_cap) {
     constexpr int T = CrossConfig<K>::THREADS;
     using NT = NibbleTables<K, T>;
     extern __shared__ __align__(16) unsigned char xsm[]; // NibbleTables<K, T>::BYTES | result tile | candidate chunk (chunk + 32 B)
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(CrossConfig<K>::THREADS)
     if (have) {
         const uint64_t o0 = a_off(ps, q), o1 = a_off(ps, q + 1);
         pat = ps.a_data + o0;
-        m = (uint32_t)(o1 - o0);
+        m = o1 < o0 ? 0xFFFFFFFFu : (uint32_t)min(o1 - o0, (uint64_t)0xFFFFFFFFu); // backwards offsets: "does not fit", skipped
     }
     const bool fits = m <= 32u * K; // guaranteed by the host's choice of K; oversize queries are skipped, not corrupted
     const uint32_t s = 32u * K - (fits ? m : 0u);
@@ -61,7 +61,9 @@ __global__ void __launch_bounds__(CrossConfig<K>::THREADS)
     for (uint32_t c = c_lo; c < c_hi; ++c) {
         const uint64_t b0 = b_off(ps, c), b1 = b_off(ps, c + 1);
         const uint8_t *txt = ps.b_data + b0;
-        const uint32_t n = (uint32_t)(b1 - b0);
+        // a speculative launch runs beside the offsets check: it never reads past a length the host has seen (n_cap); what it
+        // writes for such a candidate is recomputed, the host re-runs any batch whose statistics exceed the cap
+        const uint32_t n = b1 < b0 ? 0u : (uint32_t)min(b1 - b0, (uint64_t)n_cap);
         uint32_t Pv[K], Mv[K];
         first_column<K>(s, Pv, Mv);
         auto step = [&](uint32_t row_h, uint32_t row_l) {

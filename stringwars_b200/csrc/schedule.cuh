@@ -21,6 +21,7 @@ struct ScheduleStats {
     uint32_t max_n[SCHED_MCLASSES];
     uint32_t min_m, min_n;
     uint32_t bad;     // strings whose offsets run backwards or span 2^32 bytes or more: the call fails with SWB_INVALID_ARG
+    uint32_t extra_max; // longest string of the extra offsets array (the candidates of a cross product)
     uint32_t ticket;  // blocks that have merged their counters (device copy only)
     uint32_t seq;     // host copy only: sequence number of the call whose counters are complete
 };
@@ -51,21 +52,22 @@ __global__ void __launch_bounds__(256) schedule_count_kernel(PairSpace ps, Sched
                                                              const void *extra_offs, uint64_t extra_n, uint32_t extra32) {
     __shared__ uint32_t s_counts[SCHED_KEYS];
     __shared__ uint32_t s_max_m[SCHED_MCLASSES], s_max_n[SCHED_MCLASSES];
-    __shared__ uint32_t s_min_m, s_min_n, s_bad;
+    __shared__ uint32_t s_min_m, s_min_n, s_bad, s_extra_max;
     __shared__ bool s_last;
     for (int i = threadIdx.x; i < SCHED_KEYS; i += blockDim.x) s_counts[i] = 0;
     if (threadIdx.x < SCHED_MCLASSES) s_max_m[threadIdx.x] = 0, s_max_n[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_min_m = 0xFFFFFFFFu, s_min_n = 0xFFFFFFFFu, s_bad = 0u;
+    if (threadIdx.x == 0) s_min_m = 0xFFFFFFFFu, s_min_n = 0xFFFFFFFFu, s_bad = 0u, s_extra_max = 0u;
     __syncthreads();
     // Threads keep a run (key, count, extrema) in registers and touch shared memory only when the key changes;
     // a warp whose lanes all ended on the same key merges with warp reductions and ONE set of atomics. Uniform
     // batches (every pair the same key) would otherwise serialise a million atomics on a single counter.
     int run_key = -1;
-    uint32_t bad = 0;
+    uint32_t bad = 0, extra_max = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < extra_n && extra_offs; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t o0 = extra32 ? (uint64_t)reinterpret_cast<const uint32_t *>(extra_offs)[i] : reinterpret_cast<const uint64_t *>(extra_offs)[i];
         const uint64_t o1 = extra32 ? (uint64_t)reinterpret_cast<const uint32_t *>(extra_offs)[i + 1] : reinterpret_cast<const uint64_t *>(extra_offs)[i + 1];
         if (o1 < o0 || ((o1 - o0) >> 32) != 0u) ++bad;
+        else extra_max = max(extra_max, (uint32_t)(o1 - o0));
     }
     uint32_t run_count = 0, run_max_m = 0, run_max_n = 0, run_min_m = 0xFFFFFFFFu, run_min_n = 0xFFFFFFFFu;
     auto flush = [&](int key, uint32_t count, uint32_t mx_m, uint32_t mx_n, uint32_t mn_m, uint32_t mn_n) {
@@ -108,6 +110,7 @@ __global__ void __launch_bounds__(256) schedule_count_kernel(PairSpace ps, Sched
         }
     }
     if (bad) atomicAdd(&s_bad, bad);
+    if (extra_max) atomicMax(&s_extra_max, extra_max);
     __syncthreads();
     for (int i = threadIdx.x; i < SCHED_KEYS; i += blockDim.x)
         if (s_counts[i]) atomicAdd(&stats->counts[i], s_counts[i]);
@@ -119,6 +122,7 @@ __global__ void __launch_bounds__(256) schedule_count_kernel(PairSpace ps, Sched
         atomicMin(&stats->min_m, s_min_m);
         atomicMin(&stats->min_n, s_min_n);
         if (s_bad) atomicAdd(&stats->bad, s_bad);
+        if (s_extra_max) atomicMax(&stats->extra_max, s_extra_max);
     }
     __threadfence();
     __syncthreads();
@@ -138,8 +142,8 @@ __global__ void __launch_bounds__(256) schedule_count_kernel(PairSpace ps, Sched
     }
     if (threadIdx.x == 0) {
         published->min_m = vs->min_m, published->min_n = vs->min_n;
-        published->bad = vs->bad;
-        stats->min_m = 0xFFFFFFFFu, stats->min_n = 0xFFFFFFFFu, stats->bad = 0, stats->ticket = 0;
+        published->bad = vs->bad, published->extra_max = vs->extra_max;
+        stats->min_m = 0xFFFFFFFFu, stats->min_n = 0xFFFFFFFFu, stats->bad = 0, stats->extra_max = 0, stats->ticket = 0;
     }
     __threadfence_system();
     __syncthreads();
