@@ -81,7 +81,9 @@ static void measure_throughput(const std::string &name, const BenchBudget &budge
     std::fflush(stdout);
 }
 
-// Arrow-style tape in pinned host memory (the reference: BytesTape<u64, UnifiedAlloc>, bench.rs:292-295).
+// Arrow-style tape in CUDA managed memory — the reference's own `BytesTape<u64, UnifiedAlloc>` (bench.rs:292-295): the
+// library reads it in place, no staging copy. STRINGWARS_B200_MEMORY=pinned switches tape and matrix to page-locked host
+// memory (H2D / D2H inside every call).
 struct Tape {
     uint8_t *data = nullptr;
     uint64_t *offsets = nullptr;
@@ -135,8 +137,11 @@ int main() {
     Tape tape;
     size_t total = 0;
     for (auto &t : tokens) total += t.size();
-    if (swb_host_alloc(total + 64, (void **)&tape.data, &err) != SWB_OK || swb_host_alloc((tokens.size() + 1) * 8, (void **)&tape.offsets, &err) != SWB_OK) {
-        std::fprintf(stderr, "pinned allocation failed: %s\n", err); return 1;
+    const bool pinned = std::getenv("STRINGWARS_B200_MEMORY") && std::string(std::getenv("STRINGWARS_B200_MEMORY")) == "pinned";
+    auto alloc = pinned ? swb_host_alloc : swb_unified_alloc;
+    auto release = pinned ? swb_host_free : swb_unified_free;
+    if (alloc(total + 64, (void **)&tape.data, &err) != SWB_OK || alloc((tokens.size() + 1) * 8, (void **)&tape.offsets, &err) != SWB_OK) {
+        std::fprintf(stderr, "tape allocation failed: %s\n", err); return 1;
     }
     tape.count = tokens.size();
     tape.offsets[0] = 0;
@@ -154,10 +159,20 @@ int main() {
     uint64_t sum_q = 0, sum_c = 0; // crossproduct_metrics_bytes (bench.rs:216-224)
     for (size_t i = 0; i < side; ++i) sum_q += tape.len(i), sum_c += tape.len(side + i);
     const uint64_t cells = sum_q * sum_c, bytes = sum_q + sum_c;
+    // crossproduct_metrics_chars (bench.rs:230-247): the UTF-8 engine's cells are counted in code points, i.e. bytes that
+    // are not continuation bytes (10xxxxxx)
+    auto chars_of = [&](size_t i) {
+        uint64_t n = 0;
+        for (uint64_t p = tape.offsets[i]; p < tape.offsets[i + 1]; ++p) n += (tape.data[p] & 0xC0) != 0x80;
+        return n;
+    };
+    uint64_t chars_q = 0, chars_c = 0;
+    for (size_t i = 0; i < side; ++i) chars_q += chars_of(i), chars_c += chars_of(side + i);
+    const uint64_t cells_chars = chars_q * chars_c;
     const uint64_t *q_offs = tape.offsets, *c_offs = tape.offsets + side; // zero-copy subviews [0, side) and [side, 2*side)
 
     uint64_t *matrix = nullptr;
-    if (swb_host_alloc(side * side * sizeof(uint64_t), (void **)&matrix, &err) != SWB_OK) { std::fprintf(stderr, "%s\n", err); return 1; }
+    if (alloc(side * side * sizeof(uint64_t), (void **)&matrix, &err) != SWB_OK) { std::fprintf(stderr, "%s\n", err); return 1; } // UnifiedMat (bench.rs:130)
 
     uint8_t byte_to_class[256];
     for (int i = 0; i < 256; ++i) byte_to_class[i] = (uint8_t)(i % 32); // unary_class_costs (bench.rs:98-108)
@@ -188,9 +203,20 @@ int main() {
             }
             swb_engine_t *lev8 = nullptr;
             if (swb_levenshtein_utf8_create(scope, 0, 1, 1, 1, &lev8, &err) == SWB_OK) {
+                // pre-flight: code-point distances are bounded by the two lengths in code points and, on the diagonal of a
+                // pure-ASCII batch, equal the byte engine's
+                CHECK(swb_compute_cross(lev8, tape.data, q_offs, side, tape.data, c_offs, side, matrix, side, &err_));
+                for (size_t i = 0; i < std::min<size_t>(side, 32); ++i) {
+                    const uint64_t d = matrix[i * side + i], ca = chars_of(i), cb = chars_of(side + i);
+                    if (d > std::max(ca, cb) || d < (ca > cb ? ca - cb : cb - ca)) { std::fprintf(stderr, "utf8 pre-flight: pair %zu distance %llu outside [%llu, %llu]\n", i, (unsigned long long)d, (unsigned long long)(ca > cb ? ca - cb : cb - ca), (unsigned long long)std::max(ca, cb)); return 3; }
+                    if (chars_q == sum_q && chars_c == sum_c) {
+                        const uint64_t b = swb_levenshtein_pair(lev8, tape.data + q_offs[i], tape.len(i), tape.data + c_offs[i], tape.len(side + i), &err);
+                        if (b != d) { std::fprintf(stderr, "utf8 pre-flight mismatch on pair %zu\n", i); return 3; }
+                    }
+                }
                 measure_throughput("uniform/stringwars_b200::levenshtein_utf8" + tag, budget, [&] {
                     CHECK(swb_compute_cross(lev8, tape.data, q_offs, side, tape.data, c_offs, side, matrix, side, &err_));
-                    return WorkUnits{cells, bytes}; // byte-length cells: an upper bound of the char-length cells (bench.rs:230-247)
+                    return WorkUnits{cells_chars, bytes}; // crossproduct_metrics_chars (bench.rs:612)
                 });
                 swb_engine_destroy(lev8);
             }
@@ -221,6 +247,6 @@ int main() {
     uint64_t checksum = 0;
     for (size_t i = 0; i < side * side; ++i) checksum += matrix[i];
     std::fprintf(stderr, "  last matrix checksum=%llu\n", (unsigned long long)checksum); // cf. bench.py:305, 622
-    swb_host_free(matrix), swb_host_free(tape.data), swb_host_free(tape.offsets);
+    release(matrix), release(tape.data), release(tape.offsets);
     return 0;
 }

@@ -304,21 +304,29 @@ __global__ void __launch_bounds__(LOAD_THREADS) load_phase_simple_kernel(PairSpa
         if (bytes_a) bulk_g2s(s_a, ga - mis_a, bytes_a, &mbar);
         if (bytes_b) bulk_g2s(s_b, gb - mis_b, bytes_b, &mbar);
     }
-    const uint64_t p = p0 + threadIdx.x;
+    // A tile of fewer pairs than threads (long strings) gives each pair TPP = LOAD_THREADS / tile_pairs threads: every
+    // thread byte-sums its slice of the pair's two spans and the group adds up with shuffles, so the time a block spends
+    // reading shared memory does not grow with the string length (256-byte strings: 4 threads per pair).
+    const uint32_t tpp = max(1u, (uint32_t)LOAD_THREADS / tile_pairs) > 32u ? 32u : max(1u, (uint32_t)LOAD_THREADS / tile_pairs);
+    const uint32_t sub = threadIdx.x % tpp;
+    const uint64_t p = p0 + threadIdx.x / tpp;
+    const bool mine = threadIdx.x / tpp < tile_pairs && p < p1;
     uint64_t oa0 = 0, oa1 = 0, ob0 = 0, ob1 = 0;
-    if (p < p1) oa0 = a_off(ps, p), oa1 = a_off(ps, p + 1), ob0 = b_off(ps, p), ob1 = b_off(ps, p + 1);
+    if (mine) oa0 = a_off(ps, p), oa1 = a_off(ps, p + 1), ob0 = b_off(ps, p), ob1 = b_off(ps, p + 1);
     __syncthreads(); // mbarrier init visible to every thread before anyone waits on it
     {
         uint32_t done = 0;
         while (!done)
             asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
     }
-    if (p < p1) {
-        uint32_t acc = 0;
-        acc += span_sum(s_a, mis_a + (uint32_t)(oa0 - a_lo), mis_a + (uint32_t)(oa1 - a_lo));
-        acc += span_sum(s_b, mis_b + (uint32_t)(ob0 - b_lo), mis_b + (uint32_t)(ob1 - b_lo));
-        ps.out[p] = acc;
+    uint32_t acc = 0;
+    if (mine) {
+        const uint32_t sa = mis_a + (uint32_t)(oa0 - a_lo), la = (uint32_t)(oa1 - oa0), sb = mis_b + (uint32_t)(ob0 - b_lo), lb = (uint32_t)(ob1 - ob0);
+        acc += span_sum(s_a, sa + (uint32_t)((uint64_t)la * sub / tpp), sa + (uint32_t)((uint64_t)la * (sub + 1u) / tpp));
+        acc += span_sum(s_b, sb + (uint32_t)((uint64_t)lb * sub / tpp), sb + (uint32_t)((uint64_t)lb * (sub + 1u) / tpp));
     }
+    for (uint32_t d = tpp >> 1; d >= 1u; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (mine && sub == 0u) ps.out[p] = acc;
 }
 
 #endif // SWB_SCHEDULE_KERNELS
