@@ -232,11 +232,10 @@ swb_status_t swb::run_device_batch(swb_engine *eng, int dev_index, PairSpace ps,
 
 // ------------------------------------------------------------------------------------------ UTF-8 engine
 
-// Split one device byte tape into 32-bit symbols (count -> scan -> pack). `offs` points at n+1 offsets (u64, or u32
-// when offs32) valid with `data` (biased pointers are fine); `total_bytes` bounds the symbol count.
-static swb_status_t decode_tape(DeviceCtx &ctx, const uint8_t *data, const void *offs, uint32_t offs32, uint64_t n, uint64_t total_bytes,
-                                DeviceBuffer &sym, DeviceBuffer &sym_offs, uint32_t *d_ascii_flag, cudaStream_t stream, const char **err) {
-    SWB_CUDA(sym.reserve(total_bytes * 4 + 64));
+// Symbol offsets of one device byte tape (count -> scan): sym_offs[i] = 4 x (symbols before string i). `offs` points at
+// n+1 offsets (u64, or u32 when offs32) valid with `data` (biased pointers are fine).
+static swb_status_t count_symbols(DeviceCtx &ctx, const uint8_t *data, const void *offs, uint32_t offs32, uint64_t n, DeviceBuffer &sym_offs,
+                                  uint32_t *d_ascii_flag, cudaStream_t stream, const char **err) {
     SWB_CUDA(sym_offs.reserve((n + 1) * sizeof(uint64_t)));
     size_t tmp_bytes = 0;
     uint64_t *so = (uint64_t *)sym_offs.ptr;
@@ -247,59 +246,70 @@ static swb_status_t decode_tape(DeviceCtx &ctx, const uint8_t *data, const void 
     g_launches++;
     SWB_CUDA(cudaGetLastError());
     SWB_CUDA(cub::DeviceScan::InclusiveSum(ctx.scan_tmp.ptr, tmp_bytes, so, so, (int)(n + 1), stream));
-    utf8_pack_kernel<<<blocks, 256, 0, stream>>>(data, offs, offs32, n, so, (uint32_t *)sym.ptr);
+    return SWB_OK;
+}
+
+// The tape's symbols as 32-bit words (the wavefront kernel's input); `total_bytes` bounds the symbol count.
+static swb_status_t pack_symbols(DeviceCtx &ctx, const uint8_t *data, const void *offs, uint32_t offs32, uint64_t n, uint64_t total_bytes,
+                                 DeviceBuffer &sym, const DeviceBuffer &sym_offs, cudaStream_t stream, const char **err) {
+    SWB_CUDA(sym.reserve(total_bytes * 4 + 64));
+    const unsigned blocks = (unsigned)((n * 32 + 255) / 256);
+    utf8_pack_kernel<<<blocks, 256, 0, stream>>>(data, offs, offs32, n, (const uint64_t *)sym_offs.ptr, (uint32_t *)sym.ptr);
     g_launches++;
     SWB_CUDA(cudaGetLastError());
     return SWB_OK;
 }
 
-// Codepoint-level batch: decode both tapes, then either the byte kernels (all-ASCII input: bytes ARE code
-// points) or the kernels over 32-bit symbols. n_a / n_b are the string counts of the two tapes.
+// Codepoint-level batch. Pure-ASCII input takes the byte kernels as it is (bytes ARE code points). Element-wise pairs are
+// renamed to byte alphabets pair by pair (utf8_rename_kernel) and take the byte kernels too; cross products, pairs with
+// more than 255 distinct symbols and the explicit wavefront algorithm run the wavefront kernel over 32-bit symbols.
+// n_a / n_b are the string counts of the two tapes.
 swb_status_t swb::run_device_batch_utf8(swb_engine *eng, int dev_index, PairSpace ps, uint64_t n_a, uint64_t n_b,
                                         uint64_t a_bytes, uint64_t b_bytes, cudaStream_t stream, const char **err) {
     DeviceCtx &ctx = eng->scope->devs[dev_index];
     SWB_CUDA(ctx.flags.reserve(64));
     uint32_t *d_flag = (uint32_t *)ctx.flags.ptr;
     SWB_CUDA(cudaMemsetAsync(d_flag, 0x01, sizeof(uint32_t), stream));
+    SWB_CUDA(cudaMemsetAsync(d_flag + 1, 0, sizeof(uint32_t), stream));
     swb_status_t st;
-    if ((st = decode_tape(ctx, ps.a_data, ps.a_offs, ps.offs32 & 1u, n_a, a_bytes, ctx.sym_a, ctx.sym_a_offs, d_flag, stream, err)) != SWB_OK) return st;
-    const bool same_tape = ps.a_data == ps.b_data && ps.a_offs == ps.b_offs && n_a == n_b && ((ps.offs32 & 1u) == ((ps.offs32 >> 1) & 1u));
-    if (!same_tape)
-        if ((st = decode_tape(ctx, ps.b_data, ps.b_offs, (ps.offs32 >> 1) & 1u, n_b, b_bytes, ctx.sym_b, ctx.sym_b_offs, d_flag, stream, err)) != SWB_OK) return st;
-    uint32_t h_flag = 0;
-    SWB_CUDA(cudaMemcpyAsync(&h_flag, d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    SWB_CUDA(cudaStreamSynchronize(stream));
-    if (h_flag != 0) return run_device_batch(eng, dev_index, ps, stream, err); // pure ASCII
-    PairSpace sym = ps;
-    sym.a_data = (const uint8_t *)ctx.sym_a.ptr, sym.a_offs = (const uint64_t *)ctx.sym_a_offs.ptr;
-    sym.b_data = same_tape ? sym.a_data : (const uint8_t *)ctx.sym_b.ptr;
-    sym.b_offs = same_tape ? sym.a_offs : (const uint64_t *)ctx.sym_b_offs.ptr;
-    sym.len_shift = 2, sym.offs32 = 0;
-    // Element-wise pairs: rename every pair's symbols to a byte alphabet (utf8_remap_kernel) and run the byte kernels. A
-    // pair with more than 255 distinct symbols in its shorter string keeps the whole batch on the 32-bit wavefront kernel.
-    if (ps.n_c == 0 && eng->algorithm != SWB_ALGO_WAVEFRONT) {
+    const uint32_t a32 = ps.offs32 & 1u, b32 = (ps.offs32 >> 1) & 1u;
+    if ((st = count_symbols(ctx, ps.a_data, ps.a_offs, a32, n_a, ctx.sym_a_offs, d_flag, stream, err)) != SWB_OK) return st;
+    const bool same_tape = ps.a_data == ps.b_data && ps.a_offs == ps.b_offs && n_a == n_b && a32 == b32;
+    if (!same_tape && (st = count_symbols(ctx, ps.b_data, ps.b_offs, b32, n_b, ctx.sym_b_offs, d_flag, stream, err)) != SWB_OK) return st;
+    const uint64_t *a_so = (const uint64_t *)ctx.sym_a_offs.ptr, *b_so = same_tape ? a_so : (const uint64_t *)ctx.sym_b_offs.ptr;
+    // the rename pass goes out before the host knows whether the batch is ASCII: for ASCII text it is wasted work that
+    // nobody waits for twice — one readback brings both flags
+    const bool rename = ps.n_c == 0 && eng->algorithm != SWB_ALGO_WAVEFRONT;
+    if (rename) {
         SWB_CUDA(ctx.ren_a.reserve(a_bytes + 64));
         SWB_CUDA(ctx.ren_b.reserve(b_bytes + 64));
         SWB_CUDA(ctx.ren_a_offs.reserve((n_a + 1) * sizeof(uint64_t)));
         SWB_CUDA(ctx.ren_b_offs.reserve((n_b + 1) * sizeof(uint64_t)));
-        SWB_CUDA(cudaMemsetAsync(d_flag + 1, 0, sizeof(uint32_t), stream));
         const unsigned blocks = (unsigned)((ps.n_pairs + REMAP_WARPS - 1) / REMAP_WARPS);
-        utf8_remap_kernel<<<blocks, 32 * REMAP_WARPS, 0, stream>>>((const uint32_t *)sym.a_data, sym.a_offs, (const uint32_t *)sym.b_data, sym.b_offs, ps.n_pairs,
-                                                                  (uint8_t *)ctx.ren_a.ptr, (uint8_t *)ctx.ren_b.ptr, (uint64_t *)ctx.ren_a_offs.ptr,
-                                                                  (uint64_t *)ctx.ren_b_offs.ptr, d_flag + 1);
+        utf8_rename_kernel<<<blocks, 32 * REMAP_WARPS, 0, stream>>>(ps.a_data, ps.a_offs, a32, ps.b_data, ps.b_offs, b32, a_so, b_so, ps.n_pairs,
+                                                                   (uint8_t *)ctx.ren_a.ptr, (uint8_t *)ctx.ren_b.ptr, (uint64_t *)ctx.ren_a_offs.ptr,
+                                                                   (uint64_t *)ctx.ren_b_offs.ptr, d_flag + 1);
         g_launches++;
         SWB_CUDA(cudaGetLastError());
-        uint32_t h_overflow = 0;
-        SWB_CUDA(cudaMemcpyAsync(&h_overflow, d_flag + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-        SWB_CUDA(cudaStreamSynchronize(stream));
-        if (h_overflow == 0) {
-            PairSpace ren = ps;
-            ren.a_data = (const uint8_t *)ctx.ren_a.ptr, ren.a_offs = (const uint64_t *)ctx.ren_a_offs.ptr;
-            ren.b_data = (const uint8_t *)ctx.ren_b.ptr, ren.b_offs = (const uint64_t *)ctx.ren_b_offs.ptr;
-            ren.len_shift = 0, ren.offs32 = 0;
-            return run_device_batch(eng, dev_index, ren, stream, err);
-        }
     }
+    uint32_t h_flags[2] = {0, 0}; // [0]: batch is pure ASCII, [1]: some pair overflowed the byte alphabet
+    SWB_CUDA(cudaMemcpyAsync(h_flags, d_flag, sizeof(h_flags), cudaMemcpyDeviceToHost, stream));
+    SWB_CUDA(cudaStreamSynchronize(stream));
+    if (h_flags[0] != 0) return run_device_batch(eng, dev_index, ps, stream, err); // pure ASCII
+    if (rename && h_flags[1] == 0) {
+        PairSpace ren = ps;
+        ren.a_data = (const uint8_t *)ctx.ren_a.ptr, ren.a_offs = (const uint64_t *)ctx.ren_a_offs.ptr;
+        ren.b_data = (const uint8_t *)ctx.ren_b.ptr, ren.b_offs = (const uint64_t *)ctx.ren_b_offs.ptr;
+        ren.len_shift = 0, ren.offs32 = 0;
+        return run_device_batch(eng, dev_index, ren, stream, err);
+    }
+    if ((st = pack_symbols(ctx, ps.a_data, ps.a_offs, a32, n_a, a_bytes, ctx.sym_a, ctx.sym_a_offs, stream, err)) != SWB_OK) return st;
+    if (!same_tape && (st = pack_symbols(ctx, ps.b_data, ps.b_offs, b32, n_b, b_bytes, ctx.sym_b, ctx.sym_b_offs, stream, err)) != SWB_OK) return st;
+    PairSpace sym = ps;
+    sym.a_data = (const uint8_t *)ctx.sym_a.ptr, sym.a_offs = a_so;
+    sym.b_data = same_tape ? sym.a_data : (const uint8_t *)ctx.sym_b.ptr;
+    sym.b_offs = b_so;
+    sym.len_shift = 2, sym.offs32 = 0;
     return run_device_batch(eng, dev_index, sym, stream, err);
 }
 

@@ -10,12 +10,23 @@
 
 namespace swb {
 
-// One warp per string: bytes_out[i + 1] = 4 * (number of symbols of string i); bytes_out[0] = 0.
-// `ascii_flag` is cleared (atomicAnd) when any byte >= 0x80 is seen.
 __device__ __forceinline__ uint64_t tape_offset(const void *offs, uint32_t offs32, uint64_t i) {
     return offs32 ? (uint64_t) reinterpret_cast<const uint32_t *>(offs)[i] : reinterpret_cast<const uint64_t *>(offs)[i];
 }
 
+// Lead-byte bits of one 32-bit word: bit k is set iff byte k is NOT a continuation byte (10xxxxxx).
+__device__ __forceinline__ uint32_t lead_bits4(uint32_t w) {
+    const uint32_t cont = (w >> 7) & ~(w >> 6) & 0x01010101u; // bit 0 of byte k: byte k is 10xxxxxx
+    const uint32_t lead = cont ^ 0x01010101u;
+    return ((lead * 0x01020408u) >> 24) & 0xFu; // gather bits 0, 8, 16, 24 into a nibble
+}
+// 16 lead bits of a 16-byte piece (bit j: byte j starts a symbol).
+__device__ __forceinline__ uint32_t lead_bits16(const uint4 &p) {
+    return lead_bits4(p.x) | (lead_bits4(p.y) << 4) | (lead_bits4(p.z) << 8) | (lead_bits4(p.w) << 12);
+}
+
+// One warp per string: bytes_out[i + 1] = 4 * (number of symbols of string i); bytes_out[0] = 0.
+// `ascii_flag` is cleared (atomicAnd) when any byte >= 0x80 is seen. Lanes read re-aligned 16-byte pieces (PieceStream).
 __global__ void __launch_bounds__(256) utf8_count_kernel(const uint8_t *data, const void *offs, uint32_t offs32, uint64_t n_strings,
                                                          uint64_t *bytes_out, uint32_t *ascii_flag) {
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -23,18 +34,21 @@ __global__ void __launch_bounds__(256) utf8_count_kernel(const uint8_t *data, co
     if (warp == 0 && lane == 0) bytes_out[0] = 0;
     if (warp >= n_strings) return;
     const uint64_t o0 = tape_offset(offs, offs32, warp), o1 = tape_offset(offs, offs32, warp + 1);
-    const uint8_t *s = data + o0;
     const uint32_t len = o1 < o0 ? 0u : (uint32_t)(o1 - o0);
-    uint32_t count = 0;
-    bool high = false;
-    for (uint32_t p = lane; p < len; p += 32) {
-        const uint32_t b = ldg1(s + p);
-        count += (b & 0xC0u) != 0x80u;
-        high |= b >= 0x80u;
+    PieceStream st;
+    st.open(data + o0, len, 0u);
+    uint32_t count = 0, high = 0;
+    for (uint32_t i = lane; 16u * i < len; i += 32) {
+        const uint4 p = st.piece(i);
+        const uint32_t valid = len - 16u * i >= 16u ? 0xFFFFu : ((1u << (len - 16u * i)) - 1u);
+        count += __popc(lead_bits16(p) & valid);
+        const uint32_t hb = ((((p.x >> 7) & 0x01010101u) * 0x01020408u) >> 24 & 0xFu) | (((((p.y >> 7) & 0x01010101u) * 0x01020408u) >> 24 & 0xFu) << 4) |
+                            (((((p.z >> 7) & 0x01010101u) * 0x01020408u) >> 24 & 0xFu) << 8) | (((((p.w >> 7) & 0x01010101u) * 0x01020408u) >> 24 & 0xFu) << 12);
+        high |= hb & valid;
     }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) count += __shfl_xor_sync(0xffffffffu, count, d);
-    if (__any_sync(0xffffffffu, high) && lane == 0) atomicAnd(ascii_flag, 0u);
+    if (__any_sync(0xffffffffu, high != 0u) && lane == 0) atomicAnd(ascii_flag, 0u);
     if (lane == 0) bytes_out[warp + 1] = 4ull * count;
 }
 
@@ -81,9 +95,65 @@ constexpr uint32_t REMAP_EMPTY = 0xFFFFFFFFu; // no packed UTF-8 symbol: continu
 
 __device__ __forceinline__ uint32_t remap_hash(uint32_t key) { return (key * 0x9E3779B1u) >> (32 - 9); }
 
+// Visit the symbols of one string in order, the whole warp working on it: f(k, sym) is called by SOME lane for the k-th
+// symbol (packed lead byte + up to three continuation bytes, as utf8_pack_kernel packs them). Each lane takes a 16-byte
+// piece; the piece's symbol indices come from a warp prefix sum of the lead counts.
+template <typename F>
+__device__ __forceinline__ void for_each_symbol_warp(const uint8_t *str, uint32_t len, int lane, F &&f) {
+    PieceStream st;
+    st.open(str, len, 0u);
+    uint32_t carried = 0; // symbols before this round of 32 pieces
+    for (uint32_t base = 0; 16u * base < len; base += 32) {
+        const uint32_t i = base + (uint32_t)lane;
+        const bool live = 16u * i < len;
+        uint4 p = make_uint4(0, 0, 0, 0);
+        uint32_t ahead = 0; // the four bytes after the piece (continuation bytes of a symbol that starts near its end)
+        if (live) {
+            p = st.piece(i);
+            if (16u * (i + 1u) < len) ahead = st.piece(i + 1u).x;
+        }
+        const uint32_t remaining = live ? len - 16u * i : 0u; // bytes of the string from this piece's first byte on
+        const uint32_t valid = remaining >= 16u ? 0xFFFFu : ((1u << remaining) - 1u);
+        uint32_t leads = live ? (lead_bits16(p) & valid) : 0u;
+        const uint32_t mine = __popc(leads);
+        uint32_t before = mine; // inclusive scan over lanes
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, before, d);
+            if (lane >= d) before += up;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, before, 31);
+        uint32_t k = carried + before - mine;
+        const uint32_t words[5] = {p.x, p.y, p.z, p.w, ahead};
+        while (leads) {
+            const uint32_t j = __ffs(leads) - 1u;
+            leads &= leads - 1u;
+            // bytes j .. j + 3 of the 20-byte window
+            const uint32_t w0 = words[j >> 2], w1 = words[(j >> 2) + 1u];
+            const uint32_t four = __funnelshift_r(w0, w1, 8u * (j & 3u));
+            uint32_t sym = four & 0xFFu;
+            const uint32_t room = remaining - j; // bytes of the string from byte j on (>= 1)
+            if (room > 1u && ((four >> 8) & 0xC0u) == 0x80u) {
+                sym = (sym << 8) | ((four >> 8) & 0xFFu);
+                if (room > 2u && ((four >> 16) & 0xC0u) == 0x80u) {
+                    sym = (sym << 8) | ((four >> 16) & 0xFFu);
+                    if (room > 3u && ((four >> 24) & 0xC0u) == 0x80u) sym = (sym << 8) | (four >> 24);
+                }
+            }
+            f(k, sym);
+            ++k;
+        }
+        carried += total;
+    }
+}
+
+// Fused split + rename for element-wise pairs: reads the BYTE tapes, never materialises the 32-bit symbols.
+// a_so / b_so: 4 x (symbol offsets) from utf8_count_kernel + scan. Output: byte tapes a_out / b_out whose string i starts at
+// symbol offset a_so[i] / 4, and their u64 offsets.
 __global__ void __launch_bounds__(32 * REMAP_WARPS)
-    utf8_remap_kernel(const uint32_t *a_sym, const uint64_t *a_so, const uint32_t *b_sym, const uint64_t *b_so, uint64_t n_pairs, uint8_t *a_out,
-                      uint8_t *b_out, uint64_t *a_oo, uint64_t *b_oo, uint32_t *overflow) {
+    utf8_rename_kernel(const uint8_t *a_data, const void *a_offs, uint32_t a32, const uint8_t *b_data, const void *b_offs, uint32_t b32,
+                       const uint64_t *a_so, const uint64_t *b_so, uint64_t n_pairs, uint8_t *a_out, uint8_t *b_out, uint64_t *a_oo, uint64_t *b_oo,
+                       uint32_t *overflow) {
     __shared__ uint32_t s_keys[REMAP_WARPS][REMAP_SLOTS];
     __shared__ uint8_t s_ids[REMAP_WARPS][REMAP_SLOTS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,35 +162,35 @@ __global__ void __launch_bounds__(32 * REMAP_WARPS)
     uint32_t *keys = s_keys[warp];
     uint8_t *ids = s_ids[warp];
     const uint64_t a0 = a_so[pair] >> 2, a1 = a_so[pair + 1] >> 2, b0 = b_so[pair] >> 2, b1 = b_so[pair + 1] >> 2;
-    const uint32_t la = (uint32_t)(a1 - a0), lb = (uint32_t)(b1 - b0);
+    const uint32_t la = (uint32_t)(a1 - a0), lb = (uint32_t)(b1 - b0); // lengths in symbols
     if (lane == 0) {
         a_oo[pair] = a0, b_oo[pair] = b0;
         if (pair + 1 == n_pairs) a_oo[n_pairs] = a1, b_oo[n_pairs] = b1;
     }
+    const uint64_t ab0 = tape_offset(a_offs, a32, pair), ab1 = tape_offset(a_offs, a32, pair + 1), bb0 = tape_offset(b_offs, b32, pair),
+                   bb1 = tape_offset(b_offs, b32, pair + 1);
+    const uint8_t *a_str = a_data + ab0, *b_str = b_data + bb0;
+    const uint32_t a_len = ab1 < ab0 ? 0u : (uint32_t)(ab1 - ab0), b_len = bb1 < bb0 ? 0u : (uint32_t)(bb1 - bb0); // lengths in bytes
     const bool dict_is_a = la <= lb;
-    const uint32_t *dict = dict_is_a ? a_sym + a0 : b_sym + b0;
-    const uint32_t dict_len = dict_is_a ? la : lb;
     for (int i = lane; i < REMAP_SLOTS; i += 32) keys[i] = REMAP_EMPTY;
     __syncwarp();
     bool failed = false;
-    for (uint32_t k = lane; k < dict_len; k += 32) {
-        const uint32_t key = dict[k];
+    for_each_symbol_warp(dict_is_a ? a_str : b_str, dict_is_a ? a_len : b_len, lane, [&](uint32_t, uint32_t key) {
         uint32_t h = remap_hash(key);
         int probes = 0;
         for (; probes < REMAP_SLOTS; ++probes, h = (h + 1u) & (REMAP_SLOTS - 1)) {
+            if (keys[h] == key) break; // already there (the common case in running text): no atomic
             const uint32_t prev = atomicCAS(&keys[h], REMAP_EMPTY, key);
             if (prev == REMAP_EMPTY || prev == key) break;
         }
         failed |= probes == REMAP_SLOTS;
-    }
+    });
     __syncwarp();
-    // ids in slot order: 1 + number of occupied slots before this one
     uint32_t distinct = 0;
     for (int r = 0; r < REMAP_SLOTS / 32; ++r) {
         const bool occupied = keys[r * 32 + lane] != REMAP_EMPTY;
         const uint32_t mask = __ballot_sync(0xffffffffu, occupied);
-        const uint32_t id = distinct + __popc(mask & ((1u << lane) - 1u)) + 1u;
-        ids[r * 32 + lane] = (uint8_t)id;
+        ids[r * 32 + lane] = (uint8_t)(distinct + __popc(mask & ((1u << lane) - 1u)) + 1u);
         distinct += __popc(mask);
     }
     __syncwarp();
@@ -128,9 +198,8 @@ __global__ void __launch_bounds__(32 * REMAP_WARPS)
         if (lane == 0) atomicOr(overflow, 1u);
         return;
     }
-    auto translate = [&](const uint32_t *sym, uint32_t len, uint8_t *out) {
-        for (uint32_t k = lane; k < len; k += 32) {
-            const uint32_t key = sym[k];
+    auto translate = [&](const uint8_t *str, uint32_t len, uint8_t *out) {
+        for_each_symbol_warp(str, len, lane, [&](uint32_t k, uint32_t key) {
             uint32_t h = remap_hash(key);
             uint32_t id = 0;
             for (int probes = 0; probes < REMAP_SLOTS; ++probes, h = (h + 1u) & (REMAP_SLOTS - 1)) {
@@ -142,10 +211,10 @@ __global__ void __launch_bounds__(32 * REMAP_WARPS)
                 if (at == REMAP_EMPTY) break;
             }
             out[k] = (uint8_t)id;
-        }
+        });
     };
-    translate(a_sym + a0, la, a_out + a0);
-    translate(b_sym + b0, lb, b_out + b0);
+    translate(a_str, a_len, a_out + a0);
+    translate(b_str, b_len, b_out + b0);
 }
 
 } // namespace swb
