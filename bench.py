@@ -471,6 +471,18 @@ def run_config4(bench, sw, datasets, scope, engine, rank, local_rank, world, hos
                 "gcups": cells / (wall * 1e-3) / 1e9, "ms_per_step": wall, "device_ms": dev_total / 5, "chunks_per_shard": st["chunks"], "parity_ok": ok,
                 "parity_pairs_checked": total, "sent_bytes": st["sent_bytes"], "nvlink_gbs": st["sent_bytes"] / (wall * 1e-3) / 1e9,
                 "nvlink_frac_of_egress": st["sent_bytes"] / (wall * 1e-3) / 1e9 / NVLINK_EGRESS_GBS}
+            # ---- no scatter at all: every GPU's kernels read rank 0's tapes in place over NVLink (peer loads)
+            for _ in range(2):
+                ps = lev.compute_pairs_peer(va, vb, out.data_ptr(), _lib.RESULT_16)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                ps = lev.compute_pairs_peer(va, vb, out.data_ptr(), _lib.RESULT_16)
+            wall = (time.perf_counter() - t0) / 5 * 1e3
+            ok = bool(np.array_equal(out.cpu().numpy().astype(np.uint16).astype(np.uint64), want))
+            result["peer_loads"] = {
+                "api": "swb_compute_pairs_peer: the kernels of GPU 1..N-1 load the strings from GPU 0's memory through the NVSwitch and store their results there; no staging, no collective",
+                "gcups": cells / (wall * 1e-3) / 1e9, "ms_per_step": wall, "parity_ok": ok, "parity_pairs_checked": total, "remote_read_bytes": ps["remote_read_bytes"],
+                "nvlink_gbs": ps["remote_read_bytes"] / (wall * 1e-3) / 1e9, "nvlink_frac_of_egress": ps["remote_read_bytes"] / (wall * 1e-3) / 1e9 / NVLINK_EGRESS_GBS}
             del out
             # ---- and the harness's starting point: the whole batch in HOST memory, one call over the N-GPU scope
             h_a = sw.PinnedBuffer(total * L + 64)

@@ -251,6 +251,14 @@ SWB_API swb_status_t swb_compute_cross_tape(swb_engine_t *engine, const swb_tape
 SWB_API swb_status_t swb_compute_pairs_scatter(swb_engine_t *engine, const swb_tape_view_t *a, const swb_tape_view_t *b,
                                                void *out, swb_result_type_t out_type, double stats[4], const char **err);
 
+/* The same sharded call with NO scatter step: the kernels of every device read the root's tapes in place over NVLink
+ * (peer loads through the NVSwitch; cudaDeviceEnablePeerAccess, enabled on first use) and store their results straight
+ * into `out` on the root. Transfer and compute overlap load by load — the fused form of "scatter, then compute", with no
+ * staging buffers, no chunking and no collective. Same arguments and the same `stats` layout as
+ * swb_compute_pairs_scatter ({bytes read over NVLink, result bytes written over NVLink, milliseconds, 0}). */
+SWB_API swb_status_t swb_compute_pairs_peer(swb_engine_t *engine, const swb_tape_view_t *a, const swb_tape_view_t *b,
+                                            void *out, swb_result_type_t out_type, double stats[4], const char **err);
+
 /* Pair-load phase only: stages every pair's bytes through shared memory with the same coalesced 16-byte
  * loads the compute kernels use and writes a byte-sum per pair. Exists so the HBM-read rate of the load
  * phase can be measured on its own (BASELINE.json: ">= 60% of HBM peak on the pair-load phase"). */

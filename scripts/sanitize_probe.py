@@ -71,4 +71,48 @@ for _ in range(3):  # speculative path (second and third device-resident calls o
     lev.compute_pairs_device(ad.data_ptr(), ao.data_ptr(), bd.data_ptr(), bo.data_ptr(), 1000, out.data_ptr())
 torch.cuda.synchronize()
 check("device-resident speculative", out.cpu().numpy().view(np.uint64), orc.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets))
+# round 2: register kernel (both orientations), long alignment (global-memory variant), u32 offsets + u16 results,
+# managed tapes, resident tapes, multi-entry scope, peer-load call, load phase with several threads per pair
+a, b = datasets.words_pairs(2000, seed=3)
+want = orc.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, orc.RAPIDFUZZ_CLASS, threads=4)
+check("short (long pattern)", lev.compute_pairs(scope, a, b), want)
+a2 = datasets._ragged(rng.integers(0, 20, 500), alpha, rng, False)
+b2 = datasets._ragged(rng.integers(30, 90, 500), alpha, rng, False)
+check("short (short pattern)", lev.compute_pairs(scope, a2, b2), orc.levenshtein_pairs(a2.data, a2.offsets, b2.data, b2.offsets, orc.RAPIDFUZZ_CLASS, threads=4))
+out16 = np.zeros(len(a), np.uint16)
+lev.compute_pairs(scope, a.with_offsets(np.uint32), b.with_offsets(np.uint32), out=out16)
+check("u32 offsets, u16 results", out16.astype(np.uint64), want)
+ma, mb = BytesTape.from_arrays(a.data, a.offsets, memory="managed"), BytesTape.from_arrays(b.data, b.offsets, memory="managed")
+check("managed tapes", lev.compute_pairs(scope, ma, mb), want)
+check("resident tapes", lev.compute_pairs(scope, scope.upload(a), scope.upload(b)), want)
+la, lb = datasets._ragged(np.array([12000, 40]), alpha, rng, False), datasets._ragged(np.array([15000, 11000]), alpha, rng, False)
+nw = sw.NeedlemanWunschScores(scope, btc, costs, -5, -1)
+got = nw.compute_pairs(scope, la, lb)
+wantl = orc.align_pairs(la.data, la.offsets, lb.data, lb.offsets, btc, costs, -5, -1, threads=4)
+ok &= np.array_equal(got, wantl)
+print(f"long alignment: {'ok' if np.array_equal(got, wantl) else 'MISMATCH'} ({nw.last_kernel})", flush=True)
+multi = sw.DeviceScope.device_list([0, 0, 0])
+mlev = sw.LevenshteinDistances(multi)
+good = np.array_equal(mlev.compute_pairs(multi, a, b), want)
+ok &= good
+print("multi-entry scope:", "ok" if good else "MISMATCH", flush=True)
+from stringwars_b200 import _lib
+ad, bd = pad(a), pad(b)
+ao, bo = torch.from_numpy(a.offsets.view(np.int64).copy()).to(dev), torch.from_numpy(b.offsets.view(np.int64).copy()).to(dev)
+out = torch.zeros(len(a), dtype=torch.int64, device=dev)
+torch.cuda.synchronize()
+mlev.compute_pairs_peer(_lib.TapeView(ad.data_ptr(), ao.data_ptr(), len(a), 64), _lib.TapeView(bd.data_ptr(), bo.data_ptr(), len(b), 64), out.data_ptr(), _lib.RESULT_64)
+good = np.array_equal(out.cpu().numpy().view(np.uint64), want)
+ok &= good
+print("peer-load call:", "ok" if good else "MISMATCH", flush=True)
+a, b = datasets.ascii_pairs(500, 256)
+ad, bd = pad(a), pad(b)
+ao, bo = torch.from_numpy(a.offsets.view(np.int64).copy()).to(dev), torch.from_numpy(b.offsets.view(np.int64).copy()).to(dev)
+out = torch.zeros(500, dtype=torch.int64, device=dev)
+lev.load_phase_device(ad.data_ptr(), ao.data_ptr(), bd.data_ptr(), bo.data_ptr(), 500, out.data_ptr())
+torch.cuda.synchronize()
+want = a.data.reshape(500, 256).astype(np.int64).sum(1) + b.data.reshape(500, 256).astype(np.int64).sum(1)
+ok &= np.array_equal(out.cpu().numpy(), want)
+print("load_phase 256 B (threads per pair):", "ok" if np.array_equal(out.cpu().numpy(), want) else "MISMATCH", flush=True)
+multi.close()
 sys.exit(0 if ok else 1)

@@ -47,6 +47,8 @@ SIGNATURES = {
                                               ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, c_err]),
     "swb_compute_cross_tape": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p,
                                               ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, c_err]),
+    "swb_compute_pairs_peer": (ctypes.c_int, [ctypes.c_void_p, c_viewp, c_viewp, ctypes.c_void_p, ctypes.c_int,
+                                              ctypes.POINTER(ctypes.c_double), c_err]),
     "swb_compute_pairs_scatter": (ctypes.c_int, [ctypes.c_void_p, c_viewp, c_viewp, ctypes.c_void_p, ctypes.c_int,
                                                  ctypes.POINTER(ctypes.c_double), c_err]),
     "swb_levenshtein_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,

@@ -93,6 +93,7 @@ static void destroy_ctx(DeviceCtx &c) {
 
 namespace swb {
 void nccl_state_destroy(swb_scope *scope); // multi_gpu.cu
+void peer_state_destroy(swb_scope *scope); // multi_gpu.cu
 }
 
 static void release_engine_device_state(swb_engine *e) {
@@ -196,6 +197,7 @@ extern "C" void swb_scope_destroy(swb_scope_t *scope) {
         t->scope = nullptr;
     }
     nccl_state_destroy(scope);
+    peer_state_destroy(scope);
     for (auto &d : scope->devs) destroy_ctx(d);
     delete scope;
 }

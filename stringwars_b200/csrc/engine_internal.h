@@ -118,6 +118,7 @@ struct swb_scope {
     std::set<swb_engine *> engines; // live engines (their device state is released with the scope)
     std::set<swb_tape *> tapes;
     void *nccl = nullptr;           // multi_gpu.cu: NcclState (lazily created by the first scatter call)
+    void *peer = nullptr;           // multi_gpu.cu: PeerState (lazily created by the first peer-load call)
 };
 
 enum EngineKind { ENGINE_LEVENSHTEIN = 0, ENGINE_LEVENSHTEIN_UTF8 = 1, ENGINE_NW = 2, ENGINE_SW = 3 };

@@ -20,6 +20,7 @@
 #include "engine_internal.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <dlfcn.h>
 #include <mutex>
@@ -394,6 +395,107 @@ extern "C" swb_status_t swb_compute_pairs_scatter(swb_engine_t *engine, const sw
         SWB_CUDA(cudaSetDevice(root.device));
         SWB_CUDA(cudaEventElapsedTime(&ms, root.ev_t0, root.ev_t1));
         stats[0] = (double)sent, stats[1] = (double)gathered, stats[2] = ms, stats[3] = (double)C;
+    }
+    return SWB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ peer loads instead of a scatter
+
+namespace swb {
+struct PeerState {
+    uint64_t *h_table = nullptr, *d_table = nullptr;
+    std::vector<char> enabled;
+};
+void peer_state_destroy(swb_scope *scope) {
+    PeerState *st = (PeerState *)scope->peer;
+    if (!st) return;
+    cudaSetDevice(scope->devs[0].device);
+    if (st->h_table) cudaFreeHost(st->h_table);
+    if (st->d_table) cudaFree(st->d_table);
+    delete st;
+    scope->peer = nullptr;
+}
+} // namespace swb
+
+extern "C" swb_status_t swb_compute_pairs_peer(swb_engine_t *engine, const swb_tape_view_t *a, const swb_tape_view_t *b, void *out,
+                                               swb_result_type_t out_type, double stats[4], const char **err) {
+    swb_status_t st = check_engine_alive(engine, err);
+    if (st != SWB_OK) return st;
+    if (!a || !b || !out) return fail(err, SWB_INVALID_ARG, "NULL argument");
+    if (a->n != b->n) return fail(err, SWB_INVALID_ARG, "tapes differ in length: %zu vs %zu", a->n, b->n);
+    if ((a->offset_bits != 64 && a->offset_bits != 32) || (b->offset_bits != 64 && b->offset_bits != 32)) return fail(err, SWB_INVALID_ARG, "offset_bits must be 64 or 32");
+    if (out_type != SWB_RESULT_64 && out_type != SWB_RESULT_32 && out_type != SWB_RESULT_16) return fail(err, SWB_INVALID_ARG, "unknown result type %d", (int)out_type);
+    if (engine->kind == ENGINE_LEVENSHTEIN_UTF8) return fail(err, SWB_UNSUPPORTED, "the peer-load call runs the byte engines only");
+    const uint64_t n = a->n;
+    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    if (n == 0) return SWB_OK;
+    if (n >= 0xFFFFFFFFull) return fail(err, SWB_INVALID_ARG, "more than 2^32-1 pairs in one call");
+    swb_scope *scope = engine->scope;
+    const int D = (int)scope->devs.size();
+    if ((st = root_pointer(scope, a->data, "a.data", err)) != SWB_OK || (st = root_pointer(scope, a->offsets, "a.offsets", err)) != SWB_OK ||
+        (st = root_pointer(scope, b->data, "b.data", err)) != SWB_OK || (st = root_pointer(scope, b->offsets, "b.offsets", err)) != SWB_OK ||
+        (st = root_pointer(scope, out, "out", err)) != SWB_OK)
+        return st;
+    const uint32_t out_narrow = (uint32_t)out_type;
+    const size_t elt = result_bytes(out_narrow);
+    const uint32_t offs32 = (a->offset_bits == 32 ? 1u : 0u) | (b->offset_bits == 32 ? 2u : 0u);
+    const uint32_t aw = a->offset_bits / 8, bw = b->offset_bits / 8;
+    DeviceCtx &root = scope->devs[0];
+    PeerState *ps_state = (PeerState *)scope->peer;
+    if (!ps_state) {
+        ps_state = new PeerState();
+        ps_state->enabled.assign(D, 0);
+        scope->peer = ps_state;
+        SWB_CUDA(cudaSetDevice(root.device));
+        SWB_CUDA(cudaHostAlloc(&ps_state->h_table, 3 * (MAX_PARTS + 1) * sizeof(uint64_t), cudaHostAllocDefault));
+        SWB_CUDA(cudaMalloc(&ps_state->d_table, 3 * (MAX_PARTS + 1) * sizeof(uint64_t)));
+    }
+    for (int d = 1; d < D; ++d) {
+        if (ps_state->enabled[d]) continue;
+        DeviceCtx &ctx = scope->devs[d];
+        if (ctx.device == root.device) {
+            ps_state->enabled[d] = 1;
+            continue;
+        }
+        int can = 0;
+        SWB_CUDA(cudaDeviceCanAccessPeer(&can, ctx.device, root.device));
+        if (!can) return fail(err, SWB_UNSUPPORTED, "device %d cannot access device %d's memory", ctx.device, root.device);
+        SWB_CUDA(cudaSetDevice(ctx.device));
+        cudaError_t e = cudaDeviceEnablePeerAccess(root.device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+        else if (e != cudaSuccess) return fail(err, SWB_CUDA_ERROR, "cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", ctx.device, root.device, cudaGetErrorString(e));
+        ps_state->enabled[d] = 1;
+    }
+    SWB_CUDA(cudaSetDevice(root.device));
+    const PairSpace whole = make_pair_space(a->data, a->offsets, b->data, b->offsets, n, 0, 0, out, out_narrow, offs32);
+    // D byte-balanced shards, cut on the device (the offsets never visit the host)
+    cut_search_kernel<<<1, 64, 0, root.comm_stream>>>(whole, (uint32_t)D, ps_state->d_table);
+    g_launches++;
+    SWB_CUDA(cudaGetLastError());
+    SWB_CUDA(cudaMemcpyAsync(ps_state->h_table, ps_state->d_table, 3 * (D + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, root.comm_stream));
+    SWB_CUDA(cudaStreamSynchronize(root.comm_stream));
+    const uint64_t *cut = ps_state->h_table, *a_at = cut + (D + 1), *b_at = cut + 2 * (D + 1);
+    for (int d = 0; d < D; ++d)
+        if (cut[d + 1] < cut[d] || a_at[d + 1] < a_at[d] || b_at[d + 1] < b_at[d]) return fail(err, SWB_INVALID_ARG, "offsets are not monotonic");
+    const auto t0 = std::chrono::steady_clock::now();
+    uint64_t remote_read = 0, remote_written = 0;
+    for (int d = 0; d < D; ++d) {
+        const uint64_t cnt = cut[d + 1] - cut[d];
+        if (cnt == 0) continue;
+        DeviceCtx &ctx = scope->devs[d];
+        SWB_CUDA(cudaSetDevice(ctx.device));
+        PairSpace ps = make_pair_space(a->data, (const uint8_t *)a->offsets + cut[d] * aw, b->data, (const uint8_t *)b->offsets + cut[d] * bw, cnt, 0, 0,
+                                       (uint8_t *)out + cut[d] * elt, out_narrow, offs32);
+        if ((st = run_device_batch(engine, d, ps, ctx.compute_stream, err)) != SWB_OK) return st;
+        if (d > 0) remote_read += (a_at[d + 1] - a_at[d]) + (b_at[d + 1] - b_at[d]) + (cnt + 1) * (aw + bw), remote_written += cnt * elt;
+    }
+    for (int d = 0; d < D; ++d) {
+        SWB_CUDA(cudaSetDevice(scope->devs[d].device));
+        SWB_CUDA(cudaStreamSynchronize(scope->devs[d].compute_stream));
+    }
+    if (stats) {
+        stats[0] = (double)remote_read, stats[1] = (double)remote_written;
+        stats[2] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
     return SWB_OK;
 }

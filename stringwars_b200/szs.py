@@ -237,6 +237,15 @@ class _Engine:
             _lib.check(_lib.lib().swb_compute_cross_view(self._h, ctypes.byref(vq), ctypes.byref(vc), _ptr(matrix), stride, rtype,
                                                          ctypes.byref(err)), err)
 
+    def compute_pairs_peer(self, a_view: "_lib.TapeView", b_view: "_lib.TapeView", out_ptr: int, result_type: int = _lib.RESULT_64):
+        """The sharded call with no scatter step: every device's kernels read the root's tapes over NVLink (peer loads) and
+        write their results into `out` on the root (swb_compute_pairs_peer). Returns {remote_read_bytes, remote_written_bytes, ms}."""
+        stats = (ctypes.c_double * 4)()
+        err = ctypes.c_char_p()
+        _lib.check(_lib.lib().swb_compute_pairs_peer(self._h, ctypes.byref(a_view), ctypes.byref(b_view), out_ptr, result_type, stats,
+                                                     ctypes.byref(err)), err)
+        return {"remote_read_bytes": int(stats[0]), "remote_written_bytes": int(stats[1]), "ms": float(stats[2])}
+
     def compute_pairs_scatter(self, a_view: "_lib.TapeView", b_view: "_lib.TapeView", out_ptr: int, result_type: int = _lib.RESULT_64):
         """`LevenshteinDistances<{n}gpu>` over a batch resident on the scope's first device: one NCCL scatter, per-device
         kernels, one NCCL gather (swb_compute_pairs_scatter). Returns {sent_bytes, gathered_bytes, device_ms, chunks}."""

@@ -225,6 +225,34 @@ def test_multi_device_scope_matches_single(oracle, n_dev):
         multi.close()
 
 
+@pytest.mark.parametrize("n_dev", [1, 2, 3, 8])
+def test_peer_load_sharding(oracle, n_dev):
+    """swb_compute_pairs_peer: the batch stays on the scope's first device, every device's kernels read it in place (over
+    NVLink on a multi-GPU box; the scope's entries wrap around the devices there are otherwise) and write into `out`."""
+    import torch
+    multi = sw.DeviceScope.device_list(_scope_devices(n_dev))
+    try:
+        lev = sw.LevenshteinDistances(multi)
+        dev = torch.device("cuda", 0)
+        for (a, b), rtype, tdtype, bits in ((datasets.ascii_pairs(200_003, 64, seed=51), _lib.RESULT_16, torch.int16, 64),
+                                            (datasets.utf8_line_pairs(3001, seed=52), _lib.RESULT_64, torch.int64, 32),
+                                            (datasets.words_pairs(max(1, n_dev - 1), seed=53), _lib.RESULT_32, torch.int32, 64)):
+            want = _want(oracle, a, b)
+            ad, bd = torch.from_numpy(np.concatenate([a.data, np.zeros(64, np.uint8)])).to(dev), torch.from_numpy(np.concatenate([b.data, np.zeros(64, np.uint8)])).to(dev)
+            odt = np.int64 if bits == 64 else np.int32
+            ao, bo = torch.from_numpy(a.offsets.astype(odt)).to(dev), torch.from_numpy(b.offsets.astype(odt)).to(dev)
+            out = torch.zeros(len(a), dtype=tdtype, device=dev)
+            torch.cuda.synchronize()
+            va, vb = _lib.TapeView(ad.data_ptr(), ao.data_ptr(), len(a), bits), _lib.TapeView(bd.data_ptr(), bo.data_ptr(), len(b), bits)
+            for _ in range(2):
+                stats = lev.compute_pairs_peer(va, vb, out.data_ptr(), rtype)
+            got = out.cpu().numpy().astype(np.int64).astype(np.uint64) & np.uint64((1 << (8 * out.element_size())) - 1)
+            assert np.array_equal(got, want), (n_dev, len(a))
+            assert stats["ms"] > 0
+    finally:
+        multi.close()
+
+
 @pytest.mark.skipif(sw.device_count() < 2, reason="the NCCL scatter needs two GPUs")
 @pytest.mark.parametrize("n_dev", [2, 4, 8])
 def test_nccl_scatter_gather_inside_the_boundary(oracle, n_dev):
