@@ -7,6 +7,17 @@ nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > g
 lscpu | grep -E "Model name|^CPU\(s\)" >> gpurun_out/r2_smi.txt
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --cpu-seconds 1 --no-gates > gpurun_out/r2_bench_under_ncu.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r2_launches_utf8.csv python scripts/utf8_probe.py 100000 > /dev/null 2>&1
+python - <<PY > gpurun_out/r2_launches_utf8.txt
+import csv, collections
+rows = [r for r in csv.reader(open("gpurun_out/r2_launches_utf8.csv")) if len(r) > 10]
+hdr = rows[0]; ki = hdr.index("Kernel Name"); vi = hdr.index("Metric Value")
+agg = collections.OrderedDict()
+for r in rows[1:]:
+    k = r[ki][:70]; agg.setdefault(k, [0, 0.0]); agg[k][0] += 1; agg[k][1] += float(r[vi].replace(",", ""))
+for k, (c, t) in agg.items(): print(f"{c:4d} launches, {t / c / 1000:9.1f} us each  {k}")
+PY
+cat gpurun_out/r2_launches_utf8.txt
 NCU="ncu --set full --clock-control none --import-source on"
 cap() { # name, kernel regex, skip, command...
     local name=$1 regex=$2 skip=$3; shift 3
