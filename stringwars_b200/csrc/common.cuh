@@ -23,6 +23,7 @@ struct PairSpace {
     uint32_t len_shift;    // log2(bytes per symbol): 0 for byte tapes, 2 for decoded UTF-8 (u32 symbols)
     uint32_t out_narrow;   // 0: 64-bit results (the ABI's usize / isize); 1: 32-bit; 2: 16-bit (device staging that the host widens)
     uint32_t offs32;       // bit 0: a_offs points at u32 offsets, bit 1: b_offs does (`BytesTapeView<u32>`, AnyBytesTape::View32)
+    uint32_t idx_shift;    // string i of a pair space is string (i << idx_shift) of its tape (1: the renamed code-point tapes, whose odd strings are the gaps)
 };
 
 // Offset i of tape A / B, whatever the offset width.
@@ -61,6 +62,7 @@ __device__ __forceinline__ PairRequest pair_request(const PairSpace &ps, uint64_
         ib = k - ia * ps.n_c;
         oi = ia * ps.stride + ib;
     }
+    ia <<= ps.idx_shift, ib <<= ps.idx_shift;
     PairRequest r;
     if (ps.offs32 & 1u) {
         const uint32_t *a32 = reinterpret_cast<const uint32_t *>(ps.a_offs);

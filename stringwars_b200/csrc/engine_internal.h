@@ -194,7 +194,7 @@ inline PairSpace make_pair_space(const uint8_t *a_data, const void *a_offs, cons
     PairSpace ps;
     ps.a_data = a_data, ps.a_offs = (const uint64_t *)a_offs, ps.b_data = b_data, ps.b_offs = (const uint64_t *)b_offs;
     ps.n_pairs = n_pairs, ps.n_c = n_c, ps.stride = stride, ps.order = nullptr, ps.out = (uint64_t *)out;
-    ps.len_shift = 0, ps.out_narrow = out_narrow, ps.offs32 = offs32;
+    ps.len_shift = 0, ps.out_narrow = out_narrow, ps.offs32 = offs32, ps.idx_shift = 0;
     return ps;
 }
 static inline size_t result_bytes(uint32_t out_narrow) { return out_narrow == 0 ? 8 : (out_narrow == 1 ? 4 : 2); }

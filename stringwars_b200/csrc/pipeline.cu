@@ -260,49 +260,50 @@ static swb_status_t pack_symbols(DeviceCtx &ctx, const uint8_t *data, const void
     return SWB_OK;
 }
 
-// Codepoint-level batch. Pure-ASCII input takes the byte kernels as it is (bytes ARE code points). Element-wise pairs are
-// renamed to byte alphabets pair by pair (utf8_rename_kernel) and take the byte kernels too; cross products, pairs with
-// more than 255 distinct symbols and the explicit wavefront algorithm run the wavefront kernel over 32-bit symbols.
-// n_a / n_b are the string counts of the two tapes.
+// Codepoint-level batch. n_a / n_b are the string counts of the two tapes, a_bytes / b_bytes their byte spans.
 swb_status_t swb::run_device_batch_utf8(swb_engine *eng, int dev_index, PairSpace ps, uint64_t n_a, uint64_t n_b,
                                         uint64_t a_bytes, uint64_t b_bytes, cudaStream_t stream, const char **err) {
     DeviceCtx &ctx = eng->scope->devs[dev_index];
     SWB_CUDA(ctx.flags.reserve(64));
     uint32_t *d_flag = (uint32_t *)ctx.flags.ptr;
-    SWB_CUDA(cudaMemsetAsync(d_flag, 0x01, sizeof(uint32_t), stream));
-    SWB_CUDA(cudaMemsetAsync(d_flag + 1, 0, sizeof(uint32_t), stream));
     swb_status_t st;
     const uint32_t a32 = ps.offs32 & 1u, b32 = (ps.offs32 >> 1) & 1u;
+    // Element-wise pairs: ONE pass renames every pair to a byte alphabet (utf8_rename_kernel; pure-ASCII text goes through
+    // it like any other) and the byte kernels do the rest.
+    if (ps.n_c == 0 && eng->algorithm != SWB_ALGO_WAVEFRONT) {
+        SWB_CUDA(cudaMemsetAsync(d_flag + 1, 0, sizeof(uint32_t), stream));
+        SWB_CUDA(ctx.ren_a.reserve(a_bytes + 64));
+        SWB_CUDA(ctx.ren_b.reserve(b_bytes + 64));
+        SWB_CUDA(ctx.ren_a_offs.reserve((2 * n_a + 2) * sizeof(uint64_t)));
+        SWB_CUDA(ctx.ren_b_offs.reserve((2 * n_b + 2) * sizeof(uint64_t)));
+        const unsigned blocks = (unsigned)((ps.n_pairs + RENAME_WARPS - 1) / RENAME_WARPS);
+        utf8_rename_kernel<<<blocks, 32 * RENAME_WARPS, 0, stream>>>(ps.a_data, ps.a_offs, a32, ps.b_data, ps.b_offs, b32, ps.n_pairs, (uint8_t *)ctx.ren_a.ptr,
+                                                                    (uint8_t *)ctx.ren_b.ptr, (uint64_t *)ctx.ren_a_offs.ptr, (uint64_t *)ctx.ren_b_offs.ptr,
+                                                                    d_flag + 1);
+        g_launches++;
+        SWB_CUDA(cudaGetLastError());
+        uint32_t h_overflow = 0;
+        SWB_CUDA(cudaMemcpyAsync(&h_overflow, d_flag + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        SWB_CUDA(cudaStreamSynchronize(stream));
+        if (h_overflow == 0) {
+            PairSpace ren = ps;
+            ren.a_data = (const uint8_t *)ctx.ren_a.ptr, ren.a_offs = (const uint64_t *)ctx.ren_a_offs.ptr;
+            ren.b_data = (const uint8_t *)ctx.ren_b.ptr, ren.b_offs = (const uint64_t *)ctx.ren_b_offs.ptr;
+            ren.len_shift = 0, ren.offs32 = 0, ren.idx_shift = 1; // two strings per input string: the renamed one and the gap behind it
+            return run_device_batch(eng, dev_index, ren, stream, err);
+        }
+    }
+    // Cross products, pairs with too many distinct symbols, the explicit wavefront algorithm: 32-bit symbols
+    // (count -> scan -> pack), pure-ASCII batches excepted (bytes ARE code points: the byte kernels as they are).
+    SWB_CUDA(cudaMemsetAsync(d_flag, 0x01, sizeof(uint32_t), stream));
     if ((st = count_symbols(ctx, ps.a_data, ps.a_offs, a32, n_a, ctx.sym_a_offs, d_flag, stream, err)) != SWB_OK) return st;
     const bool same_tape = ps.a_data == ps.b_data && ps.a_offs == ps.b_offs && n_a == n_b && a32 == b32;
     if (!same_tape && (st = count_symbols(ctx, ps.b_data, ps.b_offs, b32, n_b, ctx.sym_b_offs, d_flag, stream, err)) != SWB_OK) return st;
     const uint64_t *a_so = (const uint64_t *)ctx.sym_a_offs.ptr, *b_so = same_tape ? a_so : (const uint64_t *)ctx.sym_b_offs.ptr;
-    // the rename pass goes out before the host knows whether the batch is ASCII: for ASCII text it is wasted work that
-    // nobody waits for twice — one readback brings both flags
-    const bool rename = ps.n_c == 0 && eng->algorithm != SWB_ALGO_WAVEFRONT;
-    if (rename) {
-        SWB_CUDA(ctx.ren_a.reserve(a_bytes + 64));
-        SWB_CUDA(ctx.ren_b.reserve(b_bytes + 64));
-        SWB_CUDA(ctx.ren_a_offs.reserve((n_a + 1) * sizeof(uint64_t)));
-        SWB_CUDA(ctx.ren_b_offs.reserve((n_b + 1) * sizeof(uint64_t)));
-        const unsigned blocks = (unsigned)((ps.n_pairs + REMAP_WARPS - 1) / REMAP_WARPS);
-        utf8_rename_kernel<<<blocks, 32 * REMAP_WARPS, 0, stream>>>(ps.a_data, ps.a_offs, a32, ps.b_data, ps.b_offs, b32, a_so, b_so, ps.n_pairs,
-                                                                   (uint8_t *)ctx.ren_a.ptr, (uint8_t *)ctx.ren_b.ptr, (uint64_t *)ctx.ren_a_offs.ptr,
-                                                                   (uint64_t *)ctx.ren_b_offs.ptr, d_flag + 1);
-        g_launches++;
-        SWB_CUDA(cudaGetLastError());
-    }
-    uint32_t h_flags[2] = {0, 0}; // [0]: batch is pure ASCII, [1]: some pair overflowed the byte alphabet
-    SWB_CUDA(cudaMemcpyAsync(h_flags, d_flag, sizeof(h_flags), cudaMemcpyDeviceToHost, stream));
+    uint32_t h_ascii = 0;
+    SWB_CUDA(cudaMemcpyAsync(&h_ascii, d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     SWB_CUDA(cudaStreamSynchronize(stream));
-    if (h_flags[0] != 0) return run_device_batch(eng, dev_index, ps, stream, err); // pure ASCII
-    if (rename && h_flags[1] == 0) {
-        PairSpace ren = ps;
-        ren.a_data = (const uint8_t *)ctx.ren_a.ptr, ren.a_offs = (const uint64_t *)ctx.ren_a_offs.ptr;
-        ren.b_data = (const uint8_t *)ctx.ren_b.ptr, ren.b_offs = (const uint64_t *)ctx.ren_b_offs.ptr;
-        ren.len_shift = 0, ren.offs32 = 0;
-        return run_device_batch(eng, dev_index, ren, stream, err);
-    }
+    if (h_ascii != 0) return run_device_batch(eng, dev_index, ps, stream, err);
     if ((st = pack_symbols(ctx, ps.a_data, ps.a_offs, a32, n_a, a_bytes, ctx.sym_a, ctx.sym_a_offs, stream, err)) != SWB_OK) return st;
     if (!same_tape && (st = pack_symbols(ctx, ps.b_data, ps.b_offs, b32, n_b, b_bytes, ctx.sym_b, ctx.sym_b_offs, stream, err)) != SWB_OK) return st;
     PairSpace sym = ps;

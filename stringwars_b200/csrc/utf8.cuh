@@ -7,6 +7,7 @@
 // every byte that is not 10xxxxxx; stray leading continuation bytes are ignored (same rule as the CPU oracle).
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 namespace swb {
 
@@ -81,140 +82,121 @@ __global__ void __launch_bounds__(256) utf8_pack_kernel(const uint8_t *data, con
     }
 }
 
-// Per-pair alphabet compaction: the bit-vector kernels index their match tables by BYTE, and an edit distance only ever
-// asks whether pattern symbol i equals text symbol j. So each pair's 32-bit symbols are renamed to bytes: the distinct
-// symbols of the pair's SHORTER string get ids 1, 2, ... in hash-table order, the other string is translated through the
-// same dictionary and everything it holds that the shorter string does not becomes 0 (which equals no id). The renamed
-// pair has exactly the distance of the original, and runs on the byte kernels (16+ TCUPS instead of the 32-bit
-// wavefront's 2). One warp per pair; the dictionary is an open-addressing table of REMAP_SLOTS keys in shared memory.
-// A pair whose shorter string has more than 255 distinct symbols raises `overflow` (the host then keeps the batch on the
-// 32-bit wavefront kernel).
-constexpr int REMAP_SLOTS = 512;
-constexpr int REMAP_WARPS = 4;
-constexpr uint32_t REMAP_EMPTY = 0xFFFFFFFFu; // no packed UTF-8 symbol: continuation bytes are never 0xFF
+// Per-pair alphabet compaction for element-wise pairs. The bit-vector kernels index their match tables by BYTE, and an
+// edit distance only ever asks whether pattern symbol i equals text symbol j. So each pair's code points are renamed to
+// bytes: the distinct symbols of the pair's shorter string get the number of the slot they occupy in a 255-slot
+// open-addressing dictionary (shared memory, one per warp), the other string is translated through the same dictionary
+// and everything it holds that the shorter string does not becomes 0 (which equals no id). The renamed pair has exactly
+// the distance of the original and runs on the byte kernels.
+// ONE pass over the byte tapes does everything — symbol split, dictionary, translation: a round covers 512 bytes of a
+// string (a re-aligned 16-byte piece per lane); lanes mark their lead bytes, a warp prefix sum numbers the symbols, the
+// packed symbols go to a shared-memory staging row, and the dictionary work then runs one symbol per lane, all 32 lanes
+// busy, with coalesced byte stores. There is no symbol count / scan pass: renamed string i is written at the byte offset
+// of the original string i, and the output tape has TWO strings per input string — the renamed string and the gap behind
+// it — so a PairSpace with idx_shift = 1 addresses it (out_offs[2 i] = start, out_offs[2 i + 1] = end).
+// A pair whose dictionary fills up (more than ~250 distinct code points in its shorter string) raises `overflow`; the
+// host then keeps the batch on the 32-bit wavefront kernel.
+constexpr int RENAME_WARPS = 4;
+constexpr uint32_t RENAME_SLOTS = 256;        // slot 0 is never used: ids are 1..255
+constexpr uint32_t RENAME_EMPTY = 0xFFFFFFFFu; // no packed UTF-8 symbol: continuation bytes are never 0xFF
 
-__device__ __forceinline__ uint32_t remap_hash(uint32_t key) { return (key * 0x9E3779B1u) >> (32 - 9); }
+__device__ __forceinline__ uint32_t rename_slot(uint32_t key) { return 1u + ((key * 0x9E3779B1u) >> 8) % 255u; }
 
-// Visit the symbols of one string in order, the whole warp working on it: f(k, sym) is called by SOME lane for the k-th
-// symbol (packed lead byte + up to three continuation bytes, as utf8_pack_kernel packs them). Each lane takes a 16-byte
-// piece; the piece's symbol indices come from a warp prefix sum of the lead counts.
-template <typename F>
-__device__ __forceinline__ void for_each_symbol_warp(const uint8_t *str, uint32_t len, int lane, F &&f) {
-    PieceStream st;
-    st.open(str, len, 0u);
-    uint32_t carried = 0; // symbols before this round of 32 pieces
-    for (uint32_t base = 0; 16u * base < len; base += 32) {
-        const uint32_t i = base + (uint32_t)lane;
-        const bool live = 16u * i < len;
-        uint4 p = make_uint4(0, 0, 0, 0);
-        uint32_t ahead = 0; // the four bytes after the piece (continuation bytes of a symbol that starts near its end)
-        if (live) {
-            p = st.piece(i);
-            if (16u * (i + 1u) < len) ahead = st.piece(i + 1u).x;
-        }
-        const uint32_t remaining = live ? len - 16u * i : 0u; // bytes of the string from this piece's first byte on
-        const uint32_t valid = remaining >= 16u ? 0xFFFFu : ((1u << remaining) - 1u);
-        uint32_t leads = live ? (lead_bits16(p) & valid) : 0u;
-        const uint32_t mine = __popc(leads);
-        uint32_t before = mine; // inclusive scan over lanes
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, before, d);
-            if (lane >= d) before += up;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, before, 31);
-        uint32_t k = carried + before - mine;
-        const uint32_t words[5] = {p.x, p.y, p.z, p.w, ahead};
-        while (leads) {
-            const uint32_t j = __ffs(leads) - 1u;
-            leads &= leads - 1u;
-            // bytes j .. j + 3 of the 20-byte window
-            const uint32_t w0 = words[j >> 2], w1 = words[(j >> 2) + 1u];
-            const uint32_t four = __funnelshift_r(w0, w1, 8u * (j & 3u));
-            uint32_t sym = four & 0xFFu;
-            const uint32_t room = remaining - j; // bytes of the string from byte j on (>= 1)
-            if (room > 1u && ((four >> 8) & 0xC0u) == 0x80u) {
-                sym = (sym << 8) | ((four >> 8) & 0xFFu);
-                if (room > 2u && ((four >> 16) & 0xC0u) == 0x80u) {
-                    sym = (sym << 8) | ((four >> 16) & 0xFFu);
-                    if (room > 3u && ((four >> 24) & 0xC0u) == 0x80u) sym = (sym << 8) | (four >> 24);
-                }
-            }
-            f(k, sym);
-            ++k;
-        }
-        carried += total;
-    }
-}
-
-// Fused split + rename for element-wise pairs: reads the BYTE tapes, never materialises the 32-bit symbols.
-// a_so / b_so: 4 x (symbol offsets) from utf8_count_kernel + scan. Output: byte tapes a_out / b_out whose string i starts at
-// symbol offset a_so[i] / 4, and their u64 offsets.
-__global__ void __launch_bounds__(32 * REMAP_WARPS)
-    utf8_rename_kernel(const uint8_t *a_data, const void *a_offs, uint32_t a32, const uint8_t *b_data, const void *b_offs, uint32_t b32,
-                       const uint64_t *a_so, const uint64_t *b_so, uint64_t n_pairs, uint8_t *a_out, uint8_t *b_out, uint64_t *a_oo, uint64_t *b_oo,
-                       uint32_t *overflow) {
-    __shared__ uint32_t s_keys[REMAP_WARPS][REMAP_SLOTS];
-    __shared__ uint8_t s_ids[REMAP_WARPS][REMAP_SLOTS];
+__global__ void __launch_bounds__(32 * RENAME_WARPS)
+    utf8_rename_kernel(const uint8_t *a_data, const void *a_offs, uint32_t a32, const uint8_t *b_data, const void *b_offs, uint32_t b32, uint64_t n_pairs,
+                       uint8_t *a_out, uint8_t *b_out, uint64_t *a_oo, uint64_t *b_oo, uint32_t *overflow) {
+    __shared__ uint32_t s_keys[RENAME_WARPS][RENAME_SLOTS];
+    __shared__ uint32_t s_syms[RENAME_WARPS][512];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t pair = (uint64_t)blockIdx.x * REMAP_WARPS + warp;
+    const uint64_t pair = (uint64_t)blockIdx.x * RENAME_WARPS + warp;
     if (pair >= n_pairs) return;
-    uint32_t *keys = s_keys[warp];
-    uint8_t *ids = s_ids[warp];
-    const uint64_t a0 = a_so[pair] >> 2, a1 = a_so[pair + 1] >> 2, b0 = b_so[pair] >> 2, b1 = b_so[pair + 1] >> 2;
-    const uint32_t la = (uint32_t)(a1 - a0), lb = (uint32_t)(b1 - b0); // lengths in symbols
-    if (lane == 0) {
-        a_oo[pair] = a0, b_oo[pair] = b0;
-        if (pair + 1 == n_pairs) a_oo[n_pairs] = a1, b_oo[n_pairs] = b1;
-    }
+    uint32_t *keys = s_keys[warp], *syms = s_syms[warp];
+    const uint64_t a_base = tape_offset(a_offs, a32, 0), b_base = tape_offset(b_offs, b32, 0);
     const uint64_t ab0 = tape_offset(a_offs, a32, pair), ab1 = tape_offset(a_offs, a32, pair + 1), bb0 = tape_offset(b_offs, b32, pair),
                    bb1 = tape_offset(b_offs, b32, pair + 1);
-    const uint8_t *a_str = a_data + ab0, *b_str = b_data + bb0;
-    const uint32_t a_len = ab1 < ab0 ? 0u : (uint32_t)(ab1 - ab0), b_len = bb1 < bb0 ? 0u : (uint32_t)(bb1 - bb0); // lengths in bytes
-    const bool dict_is_a = la <= lb;
-    for (int i = lane; i < REMAP_SLOTS; i += 32) keys[i] = REMAP_EMPTY;
+    const uint32_t a_len = ab1 < ab0 ? 0u : (uint32_t)(ab1 - ab0), b_len = bb1 < bb0 ? 0u : (uint32_t)(bb1 - bb0); // bytes
+    for (uint32_t i = lane; i < RENAME_SLOTS; i += 32) keys[i] = RENAME_EMPTY;
     __syncwarp();
     bool failed = false;
-    for_each_symbol_warp(dict_is_a ? a_str : b_str, dict_is_a ? a_len : b_len, lane, [&](uint32_t, uint32_t key) {
-        uint32_t h = remap_hash(key);
-        int probes = 0;
-        for (; probes < REMAP_SLOTS; ++probes, h = (h + 1u) & (REMAP_SLOTS - 1)) {
-            if (keys[h] == key) break; // already there (the common case in running text): no atomic
-            const uint32_t prev = atomicCAS(&keys[h], REMAP_EMPTY, key);
-            if (prev == REMAP_EMPTY || prev == key) break;
-        }
-        failed |= probes == REMAP_SLOTS;
-    });
-    __syncwarp();
-    uint32_t distinct = 0;
-    for (int r = 0; r < REMAP_SLOTS / 32; ++r) {
-        const bool occupied = keys[r * 32 + lane] != REMAP_EMPTY;
-        const uint32_t mask = __ballot_sync(0xffffffffu, occupied);
-        ids[r * 32 + lane] = (uint8_t)(distinct + __popc(mask & ((1u << lane) - 1u)) + 1u);
-        distinct += __popc(mask);
-    }
-    __syncwarp();
-    if (__any_sync(0xffffffffu, failed) || distinct > 255u) {
-        if (lane == 0) atomicOr(overflow, 1u);
-        return;
-    }
-    auto translate = [&](const uint8_t *str, uint32_t len, uint8_t *out) {
-        for_each_symbol_warp(str, len, lane, [&](uint32_t k, uint32_t key) {
-            uint32_t h = remap_hash(key);
-            uint32_t id = 0;
-            for (int probes = 0; probes < REMAP_SLOTS; ++probes, h = (h + 1u) & (REMAP_SLOTS - 1)) {
-                const uint32_t at = keys[h];
-                if (at == key) {
-                    id = ids[h];
-                    break;
-                }
-                if (at == REMAP_EMPTY) break;
+
+    // Renames one string; DICT: its symbols enter the dictionary. Returns the number of symbols (same in every lane).
+    auto rename = [&](const uint8_t *str, uint32_t len, uint8_t *out, auto dict_tag) -> uint32_t {
+        constexpr bool DICT = decltype(dict_tag)::value;
+        PieceStream st;
+        st.open(str, len, 0u);
+        uint32_t nsym = 0;
+        for (uint32_t base = 0; 16u * base < len; base += 32) {
+            const uint32_t i = base + (uint32_t)lane;
+            const bool live = 16u * i < len;
+            uint4 p = make_uint4(0, 0, 0, 0);
+            uint32_t ahead = 0; // the four bytes after the piece (continuation bytes of a symbol that starts near its end)
+            if (live) {
+                p = st.piece(i);
+                if (16u * (i + 1u) < len) ahead = st.piece(i + 1u).x;
             }
-            out[k] = (uint8_t)id;
-        });
+            const uint32_t remaining = live ? len - 16u * i : 0u; // bytes of the string from this piece's first byte on
+            const uint32_t valid = remaining >= 16u ? 0xFFFFu : ((1u << remaining) - 1u);
+            uint32_t leads = live ? (lead_bits16(p) & valid) : 0u;
+            const uint32_t mine = __popc(leads);
+            uint32_t upto = mine; // inclusive scan over lanes
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, upto, d);
+                if (lane >= d) upto += up;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, upto, 31);
+            uint32_t k = upto - mine;
+            const uint32_t words[5] = {p.x, p.y, p.z, p.w, ahead};
+            while (leads) { // stage this piece's packed symbols (lead byte + up to three continuation bytes, big-endian)
+                const uint32_t j = __ffs(leads) - 1u;
+                leads &= leads - 1u;
+                const uint32_t four = __funnelshift_r(words[j >> 2], words[(j >> 2) + 1u], 8u * (j & 3u)); // bytes j .. j + 3
+                uint32_t sym = four & 0xFFu;
+                const uint32_t room = remaining - j; // bytes of the string from byte j on (>= 1)
+                if (room > 1u && ((four >> 8) & 0xC0u) == 0x80u) {
+                    sym = (sym << 8) | ((four >> 8) & 0xFFu);
+                    if (room > 2u && ((four >> 16) & 0xC0u) == 0x80u) {
+                        sym = (sym << 8) | ((four >> 16) & 0xFFu);
+                        if (room > 3u && ((four >> 24) & 0xC0u) == 0x80u) sym = (sym << 8) | (four >> 24);
+                    }
+                }
+                syms[k++] = sym;
+            }
+            __syncwarp();
+            for (uint32_t q = lane; q < total; q += 32) { // one symbol per lane: dictionary lookup / insertion
+                const uint32_t key = syms[q];
+                uint32_t h = rename_slot(key), id = 0;
+                for (uint32_t probes = 0; probes < 255u; ++probes, h = h == 255u ? 1u : h + 1u) {
+                    uint32_t at = keys[h];
+                    if (DICT && at == RENAME_EMPTY) at = atomicCAS(&keys[h], RENAME_EMPTY, key) == RENAME_EMPTY ? key : keys[h];
+                    if (at == key) {
+                        id = h;
+                        break;
+                    }
+                    if (at == RENAME_EMPTY) break; // not in the dictionary: stays 0
+                }
+                if (DICT && id == 0u) failed = true; // dictionary full
+                out[nsym + q] = (uint8_t)id;
+            }
+            __syncwarp();
+            nsym += total;
+        }
+        return nsym;
     };
-    translate(a_str, a_len, a_out + a0);
-    translate(b_str, b_len, b_out + b0);
+    const bool dict_is_a = a_len <= b_len;
+    uint32_t na, nb;
+    if (dict_is_a) {
+        na = rename(a_data + ab0, a_len, a_out + (ab0 - a_base), std::true_type{});
+        nb = rename(b_data + bb0, b_len, b_out + (bb0 - b_base), std::false_type{});
+    } else {
+        nb = rename(b_data + bb0, b_len, b_out + (bb0 - b_base), std::true_type{});
+        na = rename(a_data + ab0, a_len, a_out + (ab0 - a_base), std::false_type{});
+    }
+    if (lane == 0) {
+        a_oo[2 * pair] = ab0 - a_base, a_oo[2 * pair + 1] = ab0 - a_base + na;
+        b_oo[2 * pair] = bb0 - b_base, b_oo[2 * pair + 1] = bb0 - b_base + nb;
+    }
+    if (__any_sync(0xffffffffu, failed) && lane == 0) atomicOr(overflow, 1u);
 }
 
 } // namespace swb
