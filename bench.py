@@ -691,6 +691,13 @@ def main():
             "checksum": checksum,
         }
         line.update(extra)
+        if "gates" in extra:  # the harness's own call shape next to the contract's e2e (details: gates.harness_shape)
+            h = extra["gates"]["harness_shape"]
+            line["e2e"]["harness_shape"] = {
+                "what": "side x side cross product through swb_compute_cross_view, wall time per blocking call (similarities/bench.rs:587-605); GCUPS",
+                "managed_in_place": {k: {s: h[k][s]["managed"]["gcups"] for s in h["sides"]} for k in ("acgt_100", "acgt_1k", "words")},
+                "pinned_host_u64_copies_inside": {k: {s: h[k][s]["pinned_u64"]["gcups"] for s in h["sides"]} for k in ("acgt_100", "acgt_1k", "words")},
+                "published_h100_gcups": h["published_h100_gcups"], "sides": h["sides"]}
         if cpu_gcups is not None:
             line["cpu_baseline"] = {"value": cpu_gcups, "unit": "GCUPS", "cores": host_threads, "kind": "port",
                                     "sample": f"{cpu_sample} pair evaluations of {length}x{length} in {cpu_dt:.1f} s ({len(a0)} distinct pairs repeated), rapidfuzz-class restatement (oracle/lev_oracle.c orc_rf_lev_bytes), {host_threads} threads"}
