@@ -471,6 +471,24 @@ def run_config4(bench, sw, datasets, scope, engine, rank, local_rank, world, hos
                 "gcups": cells / (wall * 1e-3) / 1e9, "ms_per_step": wall, "device_ms": dev_total / 5, "chunks_per_shard": st["chunks"], "parity_ok": ok,
                 "parity_pairs_checked": total, "sent_bytes": st["sent_bytes"], "nvlink_gbs": st["sent_bytes"] / (wall * 1e-3) / 1e9,
                 "nvlink_frac_of_egress": st["sent_bytes"] / (wall * 1e-3) / 1e9 / NVLINK_EGRESS_GBS}
+            # ---- the same call with the chunks carried by the copy engines (cudaMemcpyPeerAsync) instead of NCCL's kernels
+            ce_scope = sw.DeviceScope.gpu_devices(0, world).set_transport(sw.TRANSPORT_COPY_ENGINE)
+            ce_lev = sw.LevenshteinDistances(ce_scope)
+            out.zero_()
+            for _ in range(2):
+                st = ce_lev.compute_pairs_scatter(va, vb, out.data_ptr(), _lib.RESULT_16)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                st = ce_lev.compute_pairs_scatter(va, vb, out.data_ptr(), _lib.RESULT_16)
+            wall = (time.perf_counter() - t0) / 5 * 1e3
+            ok = bool(np.array_equal(out.cpu().numpy().astype(np.uint16).astype(np.uint64), want))
+            result["copy_engine_in_library"] = {
+                "api": "swb_compute_pairs_scatter with swb_scope_set_transport(SWB_TRANSPORT_COPY_ENGINE): same cuts / chunks / overlap, chunks moved by cudaMemcpyPeerAsync",
+                "gcups": cells / (wall * 1e-3) / 1e9, "ms_per_step": wall, "chunks_per_shard": st["chunks"], "parity_ok": ok, "parity_pairs_checked": total,
+                "sent_bytes": st["sent_bytes"], "nvlink_gbs": st["sent_bytes"] / (wall * 1e-3) / 1e9,
+                "nvlink_frac_of_egress": st["sent_bytes"] / (wall * 1e-3) / 1e9 / NVLINK_EGRESS_GBS}
+            ce_scope.close()
+            out.zero_()
             # ---- no scatter at all: every GPU's kernels read rank 0's tapes in place over NVLink (peer loads)
             for _ in range(2):
                 ps = lev.compute_pairs_peer(va, vb, out.data_ptr(), _lib.RESULT_16)

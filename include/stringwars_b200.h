@@ -251,6 +251,13 @@ SWB_API swb_status_t swb_compute_cross_tape(swb_engine_t *engine, const swb_tape
 SWB_API swb_status_t swb_compute_pairs_scatter(swb_engine_t *engine, const swb_tape_view_t *a, const swb_tape_view_t *b,
                                                void *out, swb_result_type_t out_type, double stats[4], const char **err);
 
+/* What carries the chunks of swb_compute_pairs_scatter between GPUs. NCCL (default) is what the north_star names: grouped
+ * ncclSend / ncclRecv, SM-driven copies. COPY_ENGINE moves the very same chunks with cudaMemcpyPeerAsync over NVLink (DMA
+ * engines, no SMs, no communicator), one stream per destination; everything else — cuts, chunking, overlap with the
+ * kernels, the gather — is identical. */
+typedef enum swb_transport_t { SWB_TRANSPORT_NCCL = 0, SWB_TRANSPORT_COPY_ENGINE = 1 } swb_transport_t;
+SWB_API swb_status_t swb_scope_set_transport(swb_scope_t *scope, swb_transport_t transport, const char **err);
+
 /* The same sharded call with NO scatter step: the kernels of every device read the root's tapes in place over NVLink
  * (peer loads through the NVSwitch; cudaDeviceEnablePeerAccess, enabled on first use) and store their results straight
  * into `out` on the root. Transfer and compute overlap load by load — the fused form of "scatter, then compute", with no

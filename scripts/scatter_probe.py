@@ -27,7 +27,9 @@ sl.compute_pairs_device_view(va, vb, ref.data_ptr(), _lib.RESULT_16)
 torch.cuda.synchronize()
 cells = float(L) * L * total
 tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("NCCL_")) or "default NCCL settings"
-for name, fn in (("nccl scatter", lev.compute_pairs_scatter), ("peer loads", lev.compute_pairs_peer)):
+ce_scope = sw.DeviceScope.gpu_devices(0, n_gpus).set_transport(sw.TRANSPORT_COPY_ENGINE)
+ce_lev = sw.LevenshteinDistances(ce_scope)
+for name, fn in (("nccl scatter", lev.compute_pairs_scatter), ("copy-engine scatter", ce_lev.compute_pairs_scatter), ("peer loads", lev.compute_pairs_peer)):
     for _ in range(2):
         st = fn(va, vb, out.data_ptr(), _lib.RESULT_16)
     t0 = time.perf_counter()

@@ -6,7 +6,7 @@ and fails loudly if it is missing or no GPU is present — there is no CPU fallb
 """
 from ._lib import Error, LIB_PATH  # noqa: F401
 from .szs import (  # noqa: F401
-    ALGO_AUTO, ALGO_BITPARALLEL, ALGO_WAVEFRONT, GAP_BIO, GAP_STRINGZILLA,
+    ALGO_AUTO, ALGO_BITPARALLEL, ALGO_WAVEFRONT, GAP_BIO, GAP_STRINGZILLA, TRANSPORT_COPY_ENGINE, TRANSPORT_NCCL,
     DeviceScope, DeviceTape, LevenshteinDistances, LevenshteinDistancesUtf8, NeedlemanWunschScores, SmithWatermanScores,
     device_count, launch_count, multiprocessor_count, unary_class_costs,
 )

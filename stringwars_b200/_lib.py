@@ -29,6 +29,7 @@ SIGNATURES = {
     "swb_launch_count": (ctypes.c_uint64, []),
     "swb_scope_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), c_err]),
     "swb_scope_destroy": (None, [ctypes.c_void_p]),
+    "swb_scope_set_transport": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_err]),
     "swb_scope_num_devices": (ctypes.c_int, [ctypes.c_void_p]),
     "swb_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), c_err]),
     "swb_host_free": (None, [ctypes.c_void_p]),

@@ -202,6 +202,13 @@ extern "C" void swb_scope_destroy(swb_scope_t *scope) {
     delete scope;
 }
 
+extern "C" swb_status_t swb_scope_set_transport(swb_scope_t *scope, swb_transport_t transport, const char **err) {
+    if (!scope) return fail(err, SWB_INVALID_ARG, "scope is NULL");
+    if (transport != SWB_TRANSPORT_NCCL && transport != SWB_TRANSPORT_COPY_ENGINE) return fail(err, SWB_INVALID_ARG, "unknown transport %d", (int)transport);
+    scope->transport = transport;
+    return SWB_OK;
+}
+
 extern "C" int swb_scope_num_devices(const swb_scope_t *scope) { return scope ? (int)scope->devs.size() : 0; }
 
 extern "C" swb_status_t swb_host_alloc(size_t bytes, void **out, const char **err) {

@@ -119,6 +119,8 @@ struct swb_scope {
     std::set<swb_tape *> tapes;
     void *nccl = nullptr;           // multi_gpu.cu: NcclState (lazily created by the first scatter call)
     void *peer = nullptr;           // multi_gpu.cu: PeerState (lazily created by the first peer-load call)
+    swb_transport_t transport = SWB_TRANSPORT_NCCL; // what carries the chunks of swb_compute_pairs_scatter
+    bool peers_enabled = false;     // direct peer access root <-> every device has been enabled
 };
 
 enum EngineKind { ENGINE_LEVENSHTEIN = 0, ENGINE_LEVENSHTEIN_UTF8 = 1, ENGINE_NW = 2, ENGINE_SW = 3 };

@@ -100,6 +100,7 @@ void nccl_state_destroy(swb_scope *scope) {
             cudaSetDevice(scope->devs[i].device);
             g_nccl.CommDestroy(ns->comms[i]);
         }
+    ns->comms.clear();
     cudaSetDevice(scope->devs[0].device);
     if (ns->h_table) cudaFreeHost(ns->h_table);
     if (ns->d_table) cudaFree(ns->d_table);
@@ -115,36 +116,58 @@ void nccl_state_destroy(swb_scope *scope) {
         if (r_ != 0) return fail(err, SWB_NCCL_ERROR, "%s failed: %s", #call, g_nccl.GetErrorString(r_));      \
     } while (0)
 
-static swb_status_t nccl_state(swb_scope *scope, NcclState **out, const char **err) {
-    if (scope->nccl) {
-        *out = (NcclState *)scope->nccl;
-        return SWB_OK;
-    }
-    const char *why = "";
-    if (!load_nccl(&why)) return fail(err, SWB_NCCL_ERROR, "libnccl could not be loaded (%s); set SWB_NCCL_LIB to its path", why ? why : "?");
+// The scatter call's per-scope state; the NCCL communicator is only created when the NCCL transport is used.
+static swb_status_t nccl_state(swb_scope *scope, bool want_comm, NcclState **out, const char **err) {
     const int D = (int)scope->devs.size();
-    std::vector<int> devlist(D);
-    for (int i = 0; i < D; ++i) devlist[i] = scope->devs[i].device;
-    for (int i = 0; i < D; ++i)
-        for (int j = 0; j < i; ++j)
-            if (devlist[i] == devlist[j]) return fail(err, SWB_INVALID_ARG, "an NCCL scatter needs distinct devices; device %d appears twice in the scope", devlist[i]);
-    NcclState *ns = new NcclState();
-    ns->comms.assign(D, nullptr);
-    ncclResult_t r = g_nccl.CommInitAll(ns->comms.data(), D, devlist.data());
-    if (r != 0) {
-        delete ns;
-        return fail(err, SWB_NCCL_ERROR, "ncclCommInitAll over %d devices failed: %s", D, g_nccl.GetErrorString(r));
+    NcclState *ns = (NcclState *)scope->nccl;
+    if (!ns) {
+        ns = new NcclState();
+        scope->nccl = ns;
+        cudaError_t e = cudaSetDevice(scope->devs[0].device);
+        if (e == cudaSuccess) e = cudaHostAlloc(&ns->h_table, 3 * (MAX_PARTS + 1) * sizeof(uint64_t), cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaMalloc(&ns->d_table, 3 * (MAX_PARTS + 1) * sizeof(uint64_t));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ns->ev_root, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            nccl_state_destroy(scope);
+            return fail(err, SWB_CUDA_ERROR, "scatter state setup failed: %s", cudaGetErrorString(e));
+        }
     }
-    scope->nccl = ns;
-    cudaError_t e = cudaSetDevice(scope->devs[0].device);
-    if (e == cudaSuccess) e = cudaHostAlloc(&ns->h_table, 3 * (MAX_PARTS + 1) * sizeof(uint64_t), cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaMalloc(&ns->d_table, 3 * (MAX_PARTS + 1) * sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ns->ev_root, cudaEventDisableTiming);
-    if (e != cudaSuccess) {
-        nccl_state_destroy(scope);
-        return fail(err, SWB_CUDA_ERROR, "NCCL state setup failed: %s", cudaGetErrorString(e));
+    if (want_comm && ns->comms.empty()) {
+        const char *why = "";
+        if (!load_nccl(&why)) return fail(err, SWB_NCCL_ERROR, "libnccl could not be loaded (%s); set SWB_NCCL_LIB to its path", why ? why : "?");
+        std::vector<int> devlist(D);
+        for (int i = 0; i < D; ++i) devlist[i] = scope->devs[i].device;
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j < i; ++j)
+                if (devlist[i] == devlist[j]) return fail(err, SWB_INVALID_ARG, "an NCCL scatter needs distinct devices; device %d appears twice in the scope", devlist[i]);
+        ns->comms.assign(D, nullptr);
+        ncclResult_t r = g_nccl.CommInitAll(ns->comms.data(), D, devlist.data());
+        if (r != 0) {
+            ns->comms.clear();
+            return fail(err, SWB_NCCL_ERROR, "ncclCommInitAll over %d devices failed: %s", D, g_nccl.GetErrorString(r));
+        }
     }
     *out = ns;
+    return SWB_OK;
+}
+
+// Direct peer access between the root and every other device of the scope (both directions), enabled once.
+static swb_status_t enable_peers(swb_scope *scope, const char **err) {
+    DeviceCtx &root = scope->devs[0];
+    for (size_t d = 1; d < scope->devs.size(); ++d) {
+        DeviceCtx &ctx = scope->devs[d];
+        if (ctx.device == root.device) continue;
+        for (int dir = 0; dir < 2; ++dir) {
+            const int from = dir ? root.device : ctx.device, to = dir ? ctx.device : root.device;
+            int can = 0;
+            SWB_CUDA(cudaDeviceCanAccessPeer(&can, from, to));
+            if (!can) return fail(err, SWB_UNSUPPORTED, "device %d cannot access device %d's memory", from, to);
+            SWB_CUDA(cudaSetDevice(from));
+            cudaError_t e = cudaDeviceEnablePeerAccess(to, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+            else if (e != cudaSuccess) return fail(err, SWB_CUDA_ERROR, "cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", from, to, cudaGetErrorString(e));
+        }
+    }
     return SWB_OK;
 }
 
@@ -240,8 +263,23 @@ extern "C" swb_status_t swb_compute_pairs_scatter(swb_engine_t *engine, const sw
         if (stats) stats[2] = ms;
         return SWB_OK;
     }
+    const bool use_nccl = scope->transport == SWB_TRANSPORT_NCCL;
     NcclState *ns = nullptr;
-    if ((st = nccl_state(scope, &ns, err)) != SWB_OK) return st;
+    if ((st = nccl_state(scope, use_nccl, &ns, err)) != SWB_OK) return st;
+    if (!use_nccl) {
+        if (!scope->peers_enabled && (st = enable_peers(scope, err)) != SWB_OK) return st;
+        scope->peers_enabled = true;
+    }
+    // One chunk buffer root -> device d (arrives on d's communication stream), either transport.
+    auto send_chunk = [&](DeviceCtx &ctx, int d, void *dst, const void *src, size_t bytes) -> swb_status_t {
+        if (use_nccl) {
+            SWB_NCCL(g_nccl.Send(src, bytes, kNcclUint8, d, ns->comms[0], root.comm_stream));
+            SWB_NCCL(g_nccl.Recv(dst, bytes, kNcclUint8, 0, ns->comms[d], ctx.comm_stream));
+        } else {
+            SWB_CUDA(cudaMemcpyPeerAsync(dst, ctx.device, src, root.device, bytes, ctx.comm_stream));
+        }
+        return SWB_OK;
+    };
 
     // total bytes -> chunks per shard (about 64 MiB each: long enough for NVLink to run at rate, short enough that
     // the first kernel starts early), then the byte-balanced cut table
@@ -290,6 +328,7 @@ extern "C" swb_status_t swb_compute_pairs_scatter(swb_engine_t *engine, const sw
     SWB_CUDA(ns->rel_b.reserve((n_remote + parts + 1) * sizeof(uint32_t)));
     uint32_t *rel_a = (uint32_t *)ns->rel_a.ptr, *rel_b = (uint32_t *)ns->rel_b.ptr;
 
+    const auto wall0 = std::chrono::steady_clock::now();
     SWB_CUDA(cudaEventRecord(root.ev_t0, root.comm_stream));
     if (n_remote) {
         const dim3 grid((unsigned)std::min<uint64_t>(64, (n_remote / (parts - C) + 256) / 256), parts - C);
@@ -297,10 +336,18 @@ extern "C" swb_status_t swb_compute_pairs_scatter(swb_engine_t *engine, const sw
         g_launches++;
         SWB_CUDA(cudaGetLastError());
     }
+    if (!use_nccl) { // copy engines: the copies run on the destinations' streams, after the root has rebuilt the offsets
+        SWB_CUDA(cudaEventRecord(ns->ev_root, root.comm_stream));
+        for (int d = 1; d < D; ++d) {
+            SWB_CUDA(cudaSetDevice(scope->devs[d].device));
+            SWB_CUDA(cudaStreamWaitEvent(scope->devs[d].comm_stream, ns->ev_root, 0));
+        }
+        SWB_CUDA(cudaSetDevice(root.device));
+    }
     // scatter: chunk c of every remote shard in one group
     uint64_t sent = 0;
     for (uint32_t c = 0; c < C; ++c) {
-        SWB_NCCL(g_nccl.GroupStart());
+        if (use_nccl) SWB_NCCL(g_nccl.GroupStart());
         for (int d = 1; d < D; ++d) {
             DeviceCtx &ctx = scope->devs[d];
             const uint32_t k = d * C + c, k0 = d * C;
@@ -310,21 +357,13 @@ extern "C" swb_status_t swb_compute_pairs_scatter(swb_engine_t *engine, const sw
             uint8_t *rx_a = (uint8_t *)ctx.rx_a.ptr + (a_at[k0] & 15u) + (a_at[k] - a_at[k0]);
             uint8_t *rx_b = (uint8_t *)ctx.rx_b.ptr + (b_at[k0] & 15u) + (b_at[k] - b_at[k0]);
             const uint64_t rel_src = cut[k] - cut[C] + (k - C), rel_dst = cut[k] - cut[k0] + c;
-            if (ab) {
-                SWB_NCCL(g_nccl.Send(a->data + a_at[k], ab, kNcclUint8, d, ns->comms[0], root.comm_stream));
-                SWB_NCCL(g_nccl.Recv(rx_a, ab, kNcclUint8, 0, ns->comms[d], ctx.comm_stream));
-            }
-            if (bb) {
-                SWB_NCCL(g_nccl.Send(b->data + b_at[k], bb, kNcclUint8, d, ns->comms[0], root.comm_stream));
-                SWB_NCCL(g_nccl.Recv(rx_b, bb, kNcclUint8, 0, ns->comms[d], ctx.comm_stream));
-            }
-            SWB_NCCL(g_nccl.Send(rel_a + rel_src, (cnt + 1) * 4, kNcclUint8, d, ns->comms[0], root.comm_stream));
-            SWB_NCCL(g_nccl.Recv((uint32_t *)ctx.rx_a_offs.ptr + rel_dst, (cnt + 1) * 4, kNcclUint8, 0, ns->comms[d], ctx.comm_stream));
-            SWB_NCCL(g_nccl.Send(rel_b + rel_src, (cnt + 1) * 4, kNcclUint8, d, ns->comms[0], root.comm_stream));
-            SWB_NCCL(g_nccl.Recv((uint32_t *)ctx.rx_b_offs.ptr + rel_dst, (cnt + 1) * 4, kNcclUint8, 0, ns->comms[d], ctx.comm_stream));
+            if (ab && (st = send_chunk(ctx, d, rx_a, a->data + a_at[k], ab)) != SWB_OK) return st;
+            if (bb && (st = send_chunk(ctx, d, rx_b, b->data + b_at[k], bb)) != SWB_OK) return st;
+            if ((st = send_chunk(ctx, d, (uint32_t *)ctx.rx_a_offs.ptr + rel_dst, rel_a + rel_src, (cnt + 1) * 4)) != SWB_OK) return st;
+            if ((st = send_chunk(ctx, d, (uint32_t *)ctx.rx_b_offs.ptr + rel_dst, rel_b + rel_src, (cnt + 1) * 4)) != SWB_OK) return st;
             sent += ab + bb + 2 * (cnt + 1) * 4;
         }
-        SWB_NCCL(g_nccl.GroupEnd());
+        if (use_nccl) SWB_NCCL(g_nccl.GroupEnd());
         for (int d = 1; d < D; ++d) {
             DeviceCtx &ctx = scope->devs[d];
             if (cut[d * C + c + 1] == cut[d * C + c]) continue;
@@ -371,16 +410,20 @@ extern "C" swb_status_t swb_compute_pairs_scatter(swb_engine_t *engine, const sw
         SWB_CUDA(cudaEventRecord(ctx.ev_chunks[C], ctx.compute_stream));
         SWB_CUDA(cudaStreamWaitEvent(ctx.comm_stream, ctx.ev_chunks[C], 0));
     }
-    SWB_NCCL(g_nccl.GroupStart());
+    if (use_nccl) SWB_NCCL(g_nccl.GroupStart());
     for (int d = 1; d < D; ++d) {
         DeviceCtx &ctx = scope->devs[d];
         const uint64_t n_d = cut[(d + 1) * C] - cut[d * C];
         if (n_d == 0) continue;
-        SWB_NCCL(g_nccl.Send(ctx.rx_out.ptr, n_d * elt, kNcclUint8, 0, ns->comms[d], ctx.comm_stream));
-        SWB_NCCL(g_nccl.Recv((uint8_t *)out + cut[d * C] * elt, n_d * elt, kNcclUint8, d, ns->comms[0], root.comm_stream));
+        if (use_nccl) {
+            SWB_NCCL(g_nccl.Send(ctx.rx_out.ptr, n_d * elt, kNcclUint8, 0, ns->comms[d], ctx.comm_stream));
+            SWB_NCCL(g_nccl.Recv((uint8_t *)out + cut[d * C] * elt, n_d * elt, kNcclUint8, d, ns->comms[0], root.comm_stream));
+        } else {
+            SWB_CUDA(cudaMemcpyPeerAsync((uint8_t *)out + cut[d * C] * elt, root.device, ctx.rx_out.ptr, ctx.device, n_d * elt, ctx.comm_stream));
+        }
         gathered += n_d * elt;
     }
-    SWB_NCCL(g_nccl.GroupEnd());
+    if (use_nccl) SWB_NCCL(g_nccl.GroupEnd());
     SWB_CUDA(cudaSetDevice(root.device));
     SWB_CUDA(cudaEventRecord(ns->ev_root, root.compute_stream));
     SWB_CUDA(cudaStreamWaitEvent(root.comm_stream, ns->ev_root, 0));
@@ -394,6 +437,8 @@ extern "C" swb_status_t swb_compute_pairs_scatter(swb_engine_t *engine, const sw
         float ms = 0;
         SWB_CUDA(cudaSetDevice(root.device));
         SWB_CUDA(cudaEventElapsedTime(&ms, root.ev_t0, root.ev_t1));
+        // copy-engine transport: the last copies end on the other devices' streams, so the root's event does not see them
+        if (!use_nccl) ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
         stats[0] = (double)sent, stats[1] = (double)gathered, stats[2] = ms, stats[3] = (double)C;
     }
     return SWB_OK;
@@ -450,22 +495,8 @@ extern "C" swb_status_t swb_compute_pairs_peer(swb_engine_t *engine, const swb_t
         SWB_CUDA(cudaHostAlloc(&ps_state->h_table, 3 * (MAX_PARTS + 1) * sizeof(uint64_t), cudaHostAllocDefault));
         SWB_CUDA(cudaMalloc(&ps_state->d_table, 3 * (MAX_PARTS + 1) * sizeof(uint64_t)));
     }
-    for (int d = 1; d < D; ++d) {
-        if (ps_state->enabled[d]) continue;
-        DeviceCtx &ctx = scope->devs[d];
-        if (ctx.device == root.device) {
-            ps_state->enabled[d] = 1;
-            continue;
-        }
-        int can = 0;
-        SWB_CUDA(cudaDeviceCanAccessPeer(&can, ctx.device, root.device));
-        if (!can) return fail(err, SWB_UNSUPPORTED, "device %d cannot access device %d's memory", ctx.device, root.device);
-        SWB_CUDA(cudaSetDevice(ctx.device));
-        cudaError_t e = cudaDeviceEnablePeerAccess(root.device, 0);
-        if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
-        else if (e != cudaSuccess) return fail(err, SWB_CUDA_ERROR, "cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", ctx.device, root.device, cudaGetErrorString(e));
-        ps_state->enabled[d] = 1;
-    }
+    if (!scope->peers_enabled && (st = enable_peers(scope, err)) != SWB_OK) return st;
+    scope->peers_enabled = true;
     SWB_CUDA(cudaSetDevice(root.device));
     const PairSpace whole = make_pair_space(a->data, a->offsets, b->data, b->offsets, n, 0, 0, out, out_narrow, offs32);
     // D byte-balanced shards, cut on the device (the offsets never visit the host)

@@ -28,6 +28,7 @@ _RESULT_TYPE = {8: _lib.RESULT_64, 4: _lib.RESULT_32, 2: _lib.RESULT_16}
 
 ALGO_AUTO, ALGO_WAVEFRONT, ALGO_BITPARALLEL = 0, 1, 2
 GAP_STRINGZILLA, GAP_BIO = 0, 1
+TRANSPORT_NCCL, TRANSPORT_COPY_ENGINE = 0, 1
 
 
 def device_count() -> int:
@@ -75,6 +76,12 @@ class DeviceScope:
     def device_list(cls, devices) -> "DeviceScope":
         """Explicit ordinals; an ordinal may repeat (one GPU then plays several devices of the sharding path)."""
         return cls(devices=list(devices))
+
+    def set_transport(self, transport: int) -> "DeviceScope":
+        """What carries the chunks of `compute_pairs_scatter`: TRANSPORT_NCCL (default) or TRANSPORT_COPY_ENGINE."""
+        err = ctypes.c_char_p()
+        _lib.check(_lib.lib().swb_scope_set_transport(self._h, transport, ctypes.byref(err)), err)
+        return self
 
     def upload(self, tape: TapeLike) -> "DeviceTape":
         """Resident copy of a tape on every device of the scope (what `UnifiedAlloc` gives the reference after the

@@ -253,6 +253,33 @@ def test_peer_load_sharding(oracle, n_dev):
         multi.close()
 
 
+@pytest.mark.parametrize("n_dev", [2, 3, 8])
+def test_scatter_call_with_the_copy_engine_transport(oracle, n_dev):
+    """swb_compute_pairs_scatter with SWB_TRANSPORT_COPY_ENGINE: same cuts, chunks and gather as the NCCL form, the chunks
+    carried by cudaMemcpyPeerAsync — which also runs when the scope's entries share one GPU."""
+    import torch
+    multi = sw.DeviceScope.device_list(_scope_devices(n_dev)).set_transport(sw.TRANSPORT_COPY_ENGINE)
+    try:
+        lev = sw.LevenshteinDistances(multi)
+        dev = torch.device("cuda", 0)
+        for (a, b), rtype, tdtype in ((datasets.ascii_pairs(600_011, 256, seed=61), _lib.RESULT_16, torch.int16),
+                                      (datasets.utf8_line_pairs(4001, seed=62), _lib.RESULT_64, torch.int64),
+                                      (datasets.words_pairs(2, seed=63), _lib.RESULT_32, torch.int32)):
+            want = _want(oracle, a, b)
+            ad, bd = torch.from_numpy(a.data.copy()).to(dev), torch.from_numpy(b.data.copy()).to(dev)
+            ao, bo = torch.from_numpy(a.offsets.astype(np.int64)).to(dev), torch.from_numpy(b.offsets.astype(np.int64)).to(dev)
+            out = torch.zeros(len(a), dtype=tdtype, device=dev)
+            torch.cuda.synchronize()
+            va, vb = _lib.TapeView(ad.data_ptr(), ao.data_ptr(), len(a), 64), _lib.TapeView(bd.data_ptr(), bo.data_ptr(), len(b), 64)
+            for _ in range(2):
+                stats = lev.compute_pairs_scatter(va, vb, out.data_ptr(), rtype)
+            got = out.cpu().numpy().astype(np.int64).astype(np.uint64) & np.uint64((1 << (8 * out.element_size())) - 1)
+            assert np.array_equal(got, want), (n_dev, len(a))
+            assert stats["device_ms"] > 0 and (n_dev == 1 or stats["sent_bytes"] > 0)
+    finally:
+        multi.close()
+
+
 @pytest.mark.skipif(sw.device_count() < 2, reason="the NCCL scatter needs two GPUs")
 @pytest.mark.parametrize("n_dev", [2, 4, 8])
 def test_nccl_scatter_gather_inside_the_boundary(oracle, n_dev):
