@@ -275,7 +275,7 @@ def test_scatter_call_with_the_copy_engine_transport(oracle, n_dev):
                 stats = lev.compute_pairs_scatter(va, vb, out.data_ptr(), rtype)
             got = out.cpu().numpy().astype(np.int64).astype(np.uint64) & np.uint64((1 << (8 * out.element_size())) - 1)
             assert np.array_equal(got, want), (n_dev, len(a))
-            assert stats["device_ms"] > 0 and (n_dev == 1 or stats["sent_bytes"] > 0)
+            assert stats["device_ms"] > 0 and (len(a) < 1000 or stats["sent_bytes"] > 0)
     finally:
         multi.close()
 
