@@ -3,17 +3,42 @@
 #include "engine_internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "lev_bitpar.cuh"
 #include "lev_bitpar_coop.cuh"
 #include "lev_bitpar_cross.cuh"
+#include "lev_bitpar_ws.cuh"
 #include "lev_short.cuh"
 
 namespace swb {
 
+// Warp-specialised form of the thread-per-pair kernel (lev_bitpar_ws.cuh): builder warps fill double-buffered tables while
+// compute warps run the column loop. Persistent blocks, three per SM.
+template <int K>
+static swb_status_t launch_bitpar_ws(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count, cudaStream_t stream,
+                                     const char **err, uint32_t n_cap) {
+    const size_t smem = WsConfig<K>::SMEM;
+    SWB_CUDA(allow_smem((const void *)lev_bitpar_ws_kernel<K>, ctx.device, smem));
+    const uint64_t groups = (count + WS_COMPUTE_THREADS - 1) / WS_COMPUTE_THREADS;
+    const unsigned blocks = (unsigned)std::min<uint64_t>(groups, (uint64_t)ctx.sm_count * 3);
+    {
+        ProfileBracket bracket(eng, ctx.device, stream);
+        lev_bitpar_ws_kernel<K><<<blocks, WS_THREADS, smem, stream>>>(ps, begin, count, n_cap, (uint32_t)groups);
+    }
+    g_launches++;
+    eng->last_kernel = K == 1 ? "lev_bitpar_ws<K=1>" : "lev_bitpar_ws<K=2>";
+    SWB_CUDA(cudaGetLastError());
+    return SWB_OK;
+}
+
 template <int K>
 static swb_status_t launch_bitpar(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count,
                                   cudaStream_t stream, const char **err, uint32_t n_cap = 0xFFFFFFFFu) {
+    if constexpr (K == 2) {
+        static const bool ws_off = getenv("SWB_NO_WS") != nullptr; // A/B while the kernel is being evaluated
+        if (!ws_off && count >= 32768) return launch_bitpar_ws<K>(eng, ctx, ps, begin, count, stream, err, n_cap);
+    }
     constexpr int T = BitparConfig<K>::THREADS;
     const size_t smem = BitparConfig<K>::SMEM;
     SWB_CUDA(allow_smem((const void *)lev_bitpar_kernel<K>, ctx.device, smem));
