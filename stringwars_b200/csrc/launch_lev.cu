@@ -8,11 +8,14 @@
 #include "lev_bitpar.cuh"
 #include "lev_bitpar_coop.cuh"
 #include "lev_bitpar_cross.cuh"
+#ifdef SWB_EXPERIMENTS
 #include "lev_bitpar_ws.cuh"
+#endif
 #include "lev_short.cuh"
 
 namespace swb {
 
+#ifdef SWB_EXPERIMENTS
 // Warp-specialised form of the thread-per-pair kernel (lev_bitpar_ws.cuh): builder warps fill double-buffered tables while
 // compute warps run the column loop. Persistent blocks, three per SM.
 template <int K>
@@ -31,14 +34,19 @@ static swb_status_t launch_bitpar_ws(swb_engine *eng, DeviceCtx &ctx, const Pair
     SWB_CUDA(cudaGetLastError());
     return SWB_OK;
 }
+#endif
 
 template <int K>
 static swb_status_t launch_bitpar(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count,
                                   cudaStream_t stream, const char **err, uint32_t n_cap = 0xFFFFFFFFu) {
+#ifdef SWB_EXPERIMENTS
+    // SWB_WS=1: the warp-specialised form (lev_bitpar_ws.cuh). Measured slower than this kernel (32.0-32.6 vs 34.4 TCUPS at
+    // 64x64, profiles/r2_ws_k2.txt), so it is not dispatched by the shipped library.
     if constexpr (K == 2) {
-        static const bool ws_off = getenv("SWB_NO_WS") != nullptr; // A/B while the kernel is being evaluated
-        if (!ws_off && count >= 32768) return launch_bitpar_ws<K>(eng, ctx, ps, begin, count, stream, err, n_cap);
+        static const bool ws_on = getenv("SWB_WS") != nullptr;
+        if (ws_on && count >= 32768) return launch_bitpar_ws<K>(eng, ctx, ps, begin, count, stream, err, n_cap);
     }
+#endif
     constexpr int T = BitparConfig<K>::THREADS;
     const size_t smem = BitparConfig<K>::SMEM;
     SWB_CUDA(allow_smem((const void *)lev_bitpar_kernel<K>, ctx.device, smem));

@@ -52,8 +52,8 @@ struct WsPair {
     bool run; // the pair fits this kernel and has a non-empty pattern: tables are built, columns are run
 };
 template <int K>
-__device__ __forceinline__ WsPair ws_pair(const PairSpace &ps, uint64_t slot, uint32_t n_cap) {
-    const PairView pv = pair_at(ps, slot);
+__device__ __forceinline__ WsPair ws_pair(const PairSpace &ps, const PairRequest &rq, uint32_t n_cap) {
+    const PairView pv = pair_resolve(ps, rq);
     const bool swap = pv.la > pv.lb;
     WsPair p;
     p.pat = swap ? pv.b : pv.a, p.txt = swap ? pv.a : pv.b;
@@ -204,14 +204,22 @@ __global__ void __launch_bounds__(WS_THREADS, 3) lev_bitpar_ws_kernel(PairSpace 
     const uint32_t one = 1u + opaque0, two = 2u + opaque0;
     const uint32_t smem0 = ws_smem(ws_tbl);
     const uint32_t base[2] = {NT::base(smem0, ctid), NT::base(smem0 + (uint32_t)WsConfig<K>::TABLE_BYTES, ctid)};
+    // The offsets of a group are requested one iteration ahead of their first use: with three or four compute warps per
+    // scheduler nothing else would hide that load (and the string loads that depend on it) between two pairs.
     uint32_t it = 0;
+    PairRequest rq_next;
+    rq_next.a0 = rq_next.a1 = rq_next.b0 = rq_next.b1 = rq_next.out_index = 0;
+    if ((uint64_t)blockIdx.x * WS_COMPUTE_THREADS + ctid < count) rq_next = pair_request(ps, begin + (uint64_t)blockIdx.x * WS_COMPUTE_THREADS + ctid);
     for (uint32_t g = blockIdx.x; g < groups; g += gridDim.x, ++it) {
         const uint32_t b = it & 1u, use = it >> 1; // this is the use-th time buffer b is filled / drained
         const uint64_t local = (uint64_t)g * WS_COMPUTE_THREADS + ctid;
         const bool have = local < count;
+        const PairRequest rq = rq_next;
+        const uint64_t local_next = local + (uint64_t)gridDim.x * WS_COMPUTE_THREADS;
+        if (g + gridDim.x < groups && local_next < count) rq_next = pair_request(ps, begin + local_next);
         WsPair p;
-        p.run = false;
-        if (have) p = ws_pair<K>(ps, begin + local, n_cap);
+        p.run = false, p.m = 1u, p.n = 0u, p.out_index = 0;
+        if (have) p = ws_pair<K>(ps, rq, n_cap);
         if (builder) {
             if (use > 0) mbar_wait(&bar_empty[w][b], (use - 1u) & 1u); // the compute warp is done with the previous tables
             if (p.run) ws_build<K>(p, base[b], ctid, one);
