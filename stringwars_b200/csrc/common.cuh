@@ -41,6 +41,23 @@ __device__ __forceinline__ void store_result(const PairSpace &ps, uint64_t idx, 
     else reinterpret_cast<uint16_t *>(ps.out)[idx] = (uint16_t)v;
 }
 
+// Self-validating speculative launches. A kernel launched on the bet that a batch looks like the previous one checks every
+// pair it is given — offsets that run backwards or span 4 GiB, a pattern that does not fit the kernel, a string longer than
+// anything the host has seen — skips what fails ("miss") and keeps the batch's length extrema; the last block to finish
+// publishes {misses, extrema} into mapped host memory and re-arms the device copy. The host polls one word: no statistics
+// kernel, no second launch, no copy on the critical path of a repeated call.
+struct SpecReport {
+    uint32_t misses, max_m, max_n, min_m, min_n, ticket; // device; entry state: 0, 0, 0, ~0, ~0, 0
+};
+struct SpecPublished {
+    uint32_t misses, max_m, max_n, min_m, min_n, seq; // mapped host memory; seq is written last
+};
+struct SpecArgs {
+    SpecReport *report = nullptr; // nullptr: not a speculative launch (nothing is counted or published)
+    SpecPublished *published = nullptr;
+    uint32_t seq = 0;
+};
+
 struct PairView {
     const uint8_t *a, *b; // first byte of each string
     uint32_t la, lb;      // lengths in SYMBOLS
@@ -93,6 +110,43 @@ __device__ __forceinline__ PairView pair_resolve(const PairSpace &ps, const Pair
 }
 
 __device__ __forceinline__ PairView pair_at(const PairSpace &ps, uint64_t slot) { return pair_resolve(ps, pair_request(ps, slot)); }
+
+// Both strings of a request are well-formed: neither runs backwards nor spans 4 GiB or more.
+__device__ __forceinline__ bool request_ok(const PairRequest &r) {
+    return r.a1 >= r.a0 && r.b1 >= r.b0 && ((r.a1 - r.a0) >> 32) == 0u && ((r.b1 - r.b0) >> 32) == 0u;
+}
+
+// Tail of a speculative kernel: every thread of the block calls it once. `miss`: this thread skipped its pair; m / n: the
+// pair's shorter / longer length (ignored when `counted` is false: threads beyond the batch, skipped pairs).
+__device__ __forceinline__ void spec_finish(const SpecArgs &sa, bool miss, bool counted, uint32_t m, uint32_t n) {
+    if (!sa.report) return;
+    const uint32_t all = 0xffffffffu;
+    const uint32_t hi_m = __reduce_max_sync(all, counted ? m : 0u), hi_n = __reduce_max_sync(all, counted ? n : 0u);
+    const uint32_t lo_m = __reduce_min_sync(all, counted ? m : all), lo_n = __reduce_min_sync(all, counted ? n : all);
+    const uint32_t any_miss = __ballot_sync(all, miss);
+    if ((threadIdx.x & 31u) == 0u) { // read first: after the first blocks of a uniform batch nothing is left to update
+        volatile SpecReport *r = sa.report;
+        if (any_miss) atomicAdd(&sa.report->misses, (uint32_t)__popc(any_miss));
+        if (hi_m > r->max_m) atomicMax(&sa.report->max_m, hi_m);
+        if (hi_n > r->max_n) atomicMax(&sa.report->max_n, hi_n);
+        if (lo_m < r->min_m) atomicMin(&sa.report->min_m, lo_m);
+        if (lo_n < r->min_n) atomicMin(&sa.report->min_n, lo_n);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&sa.report->ticket, 1u) == gridDim.x * gridDim.y - 1u) {
+            __threadfence();
+            volatile SpecReport *r = sa.report;
+            sa.published->misses = r->misses, sa.published->max_m = r->max_m, sa.published->max_n = r->max_n;
+            sa.published->min_m = r->min_m, sa.published->min_n = r->min_n;
+            r->misses = 0u, r->max_m = 0u, r->max_n = 0u, r->min_m = all, r->min_n = all, r->ticket = 0u;
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t *>(&sa.published->seq) = sa.seq;
+            __threadfence_system();
+        }
+    }
+}
 
 // Read-only 16-byte / 4-byte / 1-byte global loads (LDG through the non-coherent path).
 __device__ __forceinline__ uint4 ldg16(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }

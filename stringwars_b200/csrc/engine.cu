@@ -84,6 +84,8 @@ static void destroy_ctx(DeviceCtx &c) {
     if (c.ev_t1) cudaEventDestroy(c.ev_t1);
     if (c.d_stats) cudaFree(c.d_stats);
     if (c.h_stats) cudaFreeHost(c.h_stats);
+    if (c.d_spec) cudaFree(c.d_spec);
+    if (c.h_spec) cudaFreeHost(c.h_spec);
     if (c.ev_offsets) cudaEventDestroy(c.ev_offsets);
     for (auto e : c.ev_chunks) cudaEventDestroy(e);
     for (DeviceBuffer *b : {&c.order, &c.a_data, &c.a_offs, &c.b_data, &c.b_offs, &c.out, &c.sym_a, &c.sym_a_offs, &c.sym_b, &c.sym_b_offs,
@@ -161,6 +163,16 @@ extern "C" swb_status_t swb_scope_create_devices(const int *devices, int num_dev
         if (e == cudaSuccess) {
             memset(c.h_stats, 0, sizeof(ScheduleStats));
             e = cudaHostGetDevicePointer((void **)&c.h_stats_dev, c.h_stats, 0);
+        }
+        if (e == cudaSuccess) e = cudaMalloc(&c.d_spec, sizeof(SpecReport));
+        if (e == cudaSuccess) {
+            const SpecReport armed{0u, 0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u};
+            e = cudaMemcpy(c.d_spec, &armed, sizeof(armed), cudaMemcpyHostToDevice);
+        }
+        if (e == cudaSuccess) e = cudaHostAlloc(&c.h_spec, sizeof(SpecPublished), cudaHostAllocMapped);
+        if (e == cudaSuccess) {
+            memset(c.h_spec, 0, sizeof(SpecPublished));
+            e = cudaHostGetDevicePointer((void **)&c.h_spec_dev, c.h_spec, 0);
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c.ev_offsets, cudaEventDisableTiming);
         if (e != cudaSuccess) {

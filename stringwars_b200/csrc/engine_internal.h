@@ -86,6 +86,10 @@ struct DeviceCtx {
     ScheduleStats *h_stats = nullptr;     // pinned + mapped: the schedule kernel publishes into it directly
     ScheduleStats *h_stats_dev = nullptr; // device alias of h_stats
     uint32_t stats_seq = 0;               // sequence number of the last schedule launch
+    SpecReport *d_spec = nullptr;         // device: counters of a self-validating speculative launch
+    SpecPublished *h_spec = nullptr;      // pinned + mapped: what its last block publishes
+    SpecPublished *h_spec_dev = nullptr;  // device alias of h_spec
+    uint32_t spec_seq = 0;
     cudaStream_t stats_stream = nullptr;  // stream that launch ran on (polled for errors while waiting)
     cudaEvent_t ev_offsets = nullptr;
     std::vector<cudaEvent_t> ev_chunks;
@@ -207,12 +211,13 @@ swb_status_t check_engine_alive(swb_engine *engine, const char **err);
 swb_status_t launch_lev_class(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count, uint32_t max_m,
                               uint32_t max_n, cudaStream_t stream, const char **err);
 // thread-per-pair kernel of word count K = 1, 2, 4, 8 (or the register kernel of -K pattern words) over the whole pair
-// space — the speculative launch; pairs whose longer string exceeds n_cap are skipped
+// space — the speculative launch: pairs that are malformed, do not fit, or whose longer string exceeds n_cap are skipped and
+// reported through `sa`
 swb_status_t launch_lev_bitpar(swb_engine *eng, DeviceCtx &ctx, int K, const PairSpace &ps, uint64_t begin, uint64_t count, uint32_t n_cap,
-                               cudaStream_t stream, const char **err);
+                               const SpecArgs &sa, cudaStream_t stream, const char **err);
 // cross product with per-query table reuse; max_q <= 256
 swb_status_t launch_lev_cross(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint32_t n_queries, uint32_t cands_per_block,
-                              uint32_t max_q, uint32_t n_cap, cudaStream_t stream, const char **err);
+                              uint32_t max_q, uint32_t n_cap, const SpecArgs &sa, cudaStream_t stream, const char **err);
 
 // launch_align.cu / launch_packed.cu: wavefront kernels (Levenshtein in wavefront mode, UTF-8 symbols, NW, SW).
 swb_status_t launch_wavefront(swb_engine *eng, DeviceCtx &ctx, int dev_index, const PairSpace &ps, uint64_t begin, uint64_t count,

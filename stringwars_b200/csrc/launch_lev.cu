@@ -38,7 +38,7 @@ static swb_status_t launch_bitpar_ws(swb_engine *eng, DeviceCtx &ctx, const Pair
 
 template <int K>
 static swb_status_t launch_bitpar(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count,
-                                  cudaStream_t stream, const char **err, uint32_t n_cap = 0xFFFFFFFFu) {
+                                  cudaStream_t stream, const char **err, uint32_t n_cap = 0xFFFFFFFFu, const SpecArgs &sa = SpecArgs{}) {
 #ifdef SWB_EXPERIMENTS
     // SWB_WS=1: the warp-specialised form (lev_bitpar_ws.cuh). Measured slower than this kernel (32.0-32.6 vs 34.4 TCUPS at
     // 64x64, profiles/r2_ws_k2.txt), so it is not dispatched by the shipped library.
@@ -53,7 +53,7 @@ static swb_status_t launch_bitpar(swb_engine *eng, DeviceCtx &ctx, const PairSpa
     const uint64_t blocks = (count + (uint64_t)T * BitparConfig<K>::PAIRS_PER_THREAD - 1) / ((uint64_t)T * BitparConfig<K>::PAIRS_PER_THREAD);
     {
         ProfileBracket bracket(eng, ctx.device, stream);
-        lev_bitpar_kernel<K><<<(unsigned)blocks, T, smem, stream>>>(ps, begin, count, n_cap);
+        lev_bitpar_kernel<K><<<(unsigned)blocks, T, smem, stream>>>(ps, begin, count, n_cap, sa);
     }
     g_launches++;
     static const char *names[] = {"", "lev_bitpar<K=1>", "lev_bitpar<K=2>", "", "lev_bitpar<K=4>", "", "", "", "lev_bitpar<K=8>"};
@@ -65,11 +65,11 @@ static swb_status_t launch_bitpar(swb_engine *eng, DeviceCtx &ctx, const PairSpa
 // Patterns of at most 32 bytes with the pattern's match masks derived in registers (lev_short.cuh): no tables.
 template <int W, bool LONG_PAT = false>
 static swb_status_t launch_short(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count,
-                                 cudaStream_t stream, const char **err, uint32_t n_cap = 0xFFFFFFFFu) {
+                                 cudaStream_t stream, const char **err, uint32_t n_cap = 0xFFFFFFFFu, const SpecArgs &sa = SpecArgs{}) {
     const uint64_t blocks = (count + SHORT_THREADS - 1) / SHORT_THREADS;
     {
         ProfileBracket bracket(eng, ctx.device, stream);
-        lev_short_kernel<W, LONG_PAT><<<(unsigned)blocks, SHORT_THREADS, 0, stream>>>(ps, begin, count, n_cap);
+        lev_short_kernel<W, LONG_PAT><<<(unsigned)blocks, SHORT_THREADS, 0, stream>>>(ps, begin, count, n_cap, sa);
     }
     g_launches++;
     if (LONG_PAT) eng->last_kernel = W == 2 ? "lev_short<W=2,long>" : (W == 4 ? "lev_short<W=4,long>" : "lev_short<W=6,long>");
@@ -113,7 +113,7 @@ static swb_status_t launch_bitpar_coop(swb_engine *eng, DeviceCtx &ctx, const Pa
 // Cross product with table reuse: one thread per query, candidates swept (lev_bitpar_cross.cuh).
 template <int K>
 static swb_status_t launch_bitpar_cross(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint32_t n_queries, uint32_t cands_per_block,
-                                        const char *name, uint32_t n_cap, cudaStream_t stream, const char **err) {
+                                        const char *name, uint32_t n_cap, const SpecArgs &sa, cudaStream_t stream, const char **err) {
     constexpr int T = CrossConfig<K>::THREADS;
     const uint32_t chunk = 1024;
     const size_t smem = (size_t)32 * T * K * 4 + (((size_t)T * (CROSS_TILE + 1) * 4 + 15) & ~(size_t)15) + chunk + 32;
@@ -121,7 +121,7 @@ static swb_status_t launch_bitpar_cross(swb_engine *eng, DeviceCtx &ctx, const P
     const dim3 grid((n_queries + T - 1) / T, (unsigned)((ps.n_c + cands_per_block - 1) / cands_per_block));
     {
         ProfileBracket bracket(eng, ctx.device, stream);
-        lev_bitpar_cross_kernel<K><<<grid, T, smem, stream>>>(ps, n_queries, cands_per_block, chunk, n_cap);
+        lev_bitpar_cross_kernel<K><<<grid, T, smem, stream>>>(ps, n_queries, cands_per_block, chunk, n_cap, sa);
     }
     g_launches++;
     eng->last_kernel = name;
@@ -130,29 +130,29 @@ static swb_status_t launch_bitpar_cross(swb_engine *eng, DeviceCtx &ctx, const P
 }
 
 swb_status_t launch_lev_bitpar(swb_engine *eng, DeviceCtx &ctx, int K, const PairSpace &ps, uint64_t begin, uint64_t count, uint32_t n_cap,
-                               cudaStream_t stream, const char **err) {
+                               const SpecArgs &sa, cudaStream_t stream, const char **err) {
     // K < 0 selects the register kernel of -K pattern words (-K - 10: the longer string is the pattern)
     switch (K) {
-    case -12: return launch_short<2, true>(eng, ctx, ps, begin, count, stream, err, n_cap);
-    case -14: return launch_short<4, true>(eng, ctx, ps, begin, count, stream, err, n_cap);
-    case -16: return launch_short<6, true>(eng, ctx, ps, begin, count, stream, err, n_cap);
-    case -2: return launch_short<2>(eng, ctx, ps, begin, count, stream, err, n_cap);
-    case -4: return launch_short<4>(eng, ctx, ps, begin, count, stream, err, n_cap);
-    case -6: return launch_short<6>(eng, ctx, ps, begin, count, stream, err, n_cap);
-    case 1: return launch_bitpar<1>(eng, ctx, ps, begin, count, stream, err, n_cap);
-    case 2: return launch_bitpar<2>(eng, ctx, ps, begin, count, stream, err, n_cap);
-    case 4: return launch_bitpar<4>(eng, ctx, ps, begin, count, stream, err, n_cap);
-    case 8: return launch_bitpar<8>(eng, ctx, ps, begin, count, stream, err, n_cap);
+    case -12: return launch_short<2, true>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
+    case -14: return launch_short<4, true>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
+    case -16: return launch_short<6, true>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
+    case -2: return launch_short<2>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
+    case -4: return launch_short<4>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
+    case -6: return launch_short<6>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
+    case 1: return launch_bitpar<1>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
+    case 2: return launch_bitpar<2>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
+    case 4: return launch_bitpar<4>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
+    case 8: return launch_bitpar<8>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
     }
     return fail(err, SWB_INVALID_ARG, "no bit-vector kernel of %d words", K);
 }
 
 swb_status_t launch_lev_cross(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint32_t n_queries, uint32_t cands_per_block,
-                              uint32_t max_q, uint32_t n_cap, cudaStream_t stream, const char **err) {
-    if (max_q <= 32) return launch_bitpar_cross<1>(eng, ctx, ps, n_queries, cands_per_block, "lev_bitpar_cross<K=1>", n_cap, stream, err);
-    if (max_q <= 64) return launch_bitpar_cross<2>(eng, ctx, ps, n_queries, cands_per_block, "lev_bitpar_cross<K=2>", n_cap, stream, err);
-    if (max_q <= 128) return launch_bitpar_cross<4>(eng, ctx, ps, n_queries, cands_per_block, "lev_bitpar_cross<K=4>", n_cap, stream, err);
-    return launch_bitpar_cross<8>(eng, ctx, ps, n_queries, cands_per_block, "lev_bitpar_cross<K=8>", n_cap, stream, err);
+                              uint32_t max_q, uint32_t n_cap, const SpecArgs &sa, cudaStream_t stream, const char **err) {
+    if (max_q <= 32) return launch_bitpar_cross<1>(eng, ctx, ps, n_queries, cands_per_block, "lev_bitpar_cross<K=1>", n_cap, sa, stream, err);
+    if (max_q <= 64) return launch_bitpar_cross<2>(eng, ctx, ps, n_queries, cands_per_block, "lev_bitpar_cross<K=2>", n_cap, sa, stream, err);
+    if (max_q <= 128) return launch_bitpar_cross<4>(eng, ctx, ps, n_queries, cands_per_block, "lev_bitpar_cross<K=4>", n_cap, sa, stream, err);
+    return launch_bitpar_cross<8>(eng, ctx, ps, n_queries, cands_per_block, "lev_bitpar_cross<K=8>", n_cap, sa, stream, err);
 }
 
 swb_status_t launch_lev_class(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count, uint32_t max_m,

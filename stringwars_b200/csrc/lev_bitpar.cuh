@@ -296,39 +296,40 @@ __device__ __forceinline__ void add_symbol(uint32_t base, uint32_t pos, uint32_t
 // A thread computes any pair whose pattern fits its K words and SKIPS (writes nothing for) a longer one: that is
 // what lets the host launch this kernel speculatively, before the batch's length statistics are known — the
 // statistics then tell the host whether anything was skipped (engine.cu, run_device_batch).
+// One pair; returns true when the pair was SKIPPED (malformed offsets, a pattern beyond 32 K symbols, a text longer than
+// n_cap). m_out / n_out: the pair's shorter / longer length when it was not skipped.
 template <int K>
-__global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(PairSpace ps, uint64_t begin, uint64_t count, uint32_t n_cap) {
+__device__ __forceinline__ bool lev_bitpar_pair(const PairSpace &ps, uint64_t begin, uint64_t local, uint32_t n_cap, uint32_t opaque0, uint32_t &m_out,
+                                                uint32_t &n_out) {
     constexpr int T = BitparConfig<K>::THREADS;
     using NT = NibbleTables<K, T>;
     extern __shared__ __align__(16) unsigned char tbl_bytes[]; // NibbleTables<K, T>::BYTES
     const int tid = threadIdx.x;
-    const uint64_t local = (uint64_t)blockIdx.x * T + tid;
-    if (local >= count) return;
-    // 1 and 2 as values ptxas cannot fold (count < 2^63 always): see mad_lo
-    const uint32_t opaque0 = (uint32_t)(count >> 63);
+    // 1 and 2 as values ptxas cannot fold: see mad_lo
     const uint32_t one = 1u + opaque0, two = 2u + opaque0;
     const uint32_t base_hi = NT::base((uint32_t)__cvta_generic_to_shared(tbl_bytes), tid), base_lo = base_hi + NT::TABLE;
 
+    const PairRequest pr = pair_request(ps, begin + local);
 #ifdef SWB_BITPAR_ZERO_FIRST
-    const PairRequest pr = pair_request(ps, begin + local); // offsets in flight while the tables are zeroed
-    zero_tables<K, T>(base_hi);
-    const PairView pv = pair_resolve(ps, pr);
-#else
-    const PairView pv = pair_at(ps, begin + local);
+    zero_tables<K, T>(base_hi); // offsets in flight while the tables are zeroed
 #endif
+    if (!request_ok(pr)) return true;
+    const PairView pv = pair_resolve(ps, pr);
     // pattern = shorter string (distance is symmetric), text = longer one
     const bool swap = pv.la > pv.lb;
     const uint8_t *pat = swap ? pv.b : pv.a;
     const uint8_t *txt = swap ? pv.a : pv.b;
     const uint32_t m = swap ? pv.lb : pv.la;
     const uint32_t n = swap ? pv.la : pv.lb;
+    m_out = m, n_out = n;
+    // a text longer than anything the host has seen (a speculative launch validates as it goes: it must not chase an
+    // unchecked length), or not this kernel's class (speculative launch on a batch that changed shape)
+    if (n > n_cap) return true;
     if (m == 0) {
         store_result(ps, pv.out_index, n);
-        return;
+        return false;
     }
-    // not this kernel's class (speculative launch on a batch that changed shape), or a text longer than anything the
-    // host has validated (a speculative launch runs beside the offsets check: it must not chase an unchecked length)
-    if (m > 32u * K || n > n_cap) return;
+    if (m > 32u * K) return true;
     const uint32_t s = 32u * K - m; // pattern symbol i lives at bit position s + i
 
     // ---- requests that can leave before the tables are zeroed
@@ -452,6 +453,17 @@ __global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(Pa
 #pragma unroll
     for (int w = 0; w < K; ++w) score += __popc(Pv[w]) - __popc(Mv[w]);
     store_result(ps, pv.out_index, score);
+    return false;
+}
+
+template <int K>
+__global__ void __launch_bounds__(BitparConfig<K>::THREADS) lev_bitpar_kernel(PairSpace ps, uint64_t begin, uint64_t count, uint32_t n_cap, SpecArgs sa) {
+    const uint64_t local = (uint64_t)blockIdx.x * BitparConfig<K>::THREADS + threadIdx.x;
+    const uint32_t opaque0 = (uint32_t)(count >> 63); // run-time 0 (count < 2^63 always)
+    bool miss = false;
+    uint32_t m = 0, n = 0;
+    if (local < count) miss = lev_bitpar_pair<K>(ps, begin, local, n_cap, opaque0, m, n);
+    spec_finish(sa, miss, local < count && !miss, m, n);
 }
 
 } // namespace swb

@@ -26,7 +26,7 @@ constexpr int CROSS_TILE = 16; // candidates per result tile: 16 x u64 = one 128
 
 template <int K>
 __global__ void __launch_bounds__(CrossConfig<K>::THREADS)
-    lev_bitpar_cross_kernel(PairSpace ps, uint32_t n_queries, uint32_t cands_per_block, uint32_t chunk, uint32_t n_cap) {
+    lev_bitpar_cross_kernel(PairSpace ps, uint32_t n_queries, uint32_t cands_per_block, uint32_t chunk, uint32_t n_cap, SpecArgs sa) {
     constexpr int T = CrossConfig<K>::THREADS;
     using NT = NibbleTables<K, T>;
     extern __shared__ __align__(16) unsigned char xsm[]; // NibbleTables<K, T>::BYTES | result tile | candidate chunk (chunk + 32 B)
@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(CrossConfig<K>::THREADS)
         m = o1 < o0 ? 0xFFFFFFFFu : (uint32_t)min(o1 - o0, (uint64_t)0xFFFFFFFFu); // backwards offsets: "does not fit", skipped
     }
     const bool fits = m <= 32u * K; // guaranteed by the host's choice of K; oversize queries are skipped, not corrupted
+    bool miss = have && !fits;      // speculative launches report what they skipped (spec_finish)
+    uint32_t longest_cand = 0;
     const uint32_t s = 32u * K - (fits ? m : 0u);
     if (have && fits) for_each_byte_global(pat, m, [&](uint32_t i, uint32_t c) { add_symbol<K, T>(base_hi, s + i, c); });
     const bool active = have && fits && m > 0;
@@ -64,6 +66,8 @@ __global__ void __launch_bounds__(CrossConfig<K>::THREADS)
         // a speculative launch runs beside the offsets check: it never reads past a length the host has seen (n_cap); what it
         // writes for such a candidate is recomputed, the host re-runs any batch whose statistics exceed the cap
         const uint32_t n = b1 < b0 ? 0u : (uint32_t)min(b1 - b0, (uint64_t)n_cap);
+        miss |= b1 < b0 || b1 - b0 > (uint64_t)n_cap;
+        longest_cand = max(longest_cand, n);
         uint32_t Pv[K], Mv[K];
         first_column<K>(s, Pv, Mv);
         auto step = [&](uint32_t row_h, uint32_t row_l) {
@@ -114,6 +118,8 @@ __global__ void __launch_bounds__(CrossConfig<K>::THREADS)
             __syncthreads();
         }
     }
+    // statistics in the terms the host keeps them: "m" = the query (pattern), "n" = the candidates this block saw
+    spec_finish(sa, miss, have && fits && c_hi > c_lo, m, longest_cand);
 }
 
 } // namespace swb

@@ -91,23 +91,26 @@ __device__ __forceinline__ void short_columns(const uint32_t (&pat)[W], const ui
 // longest shorter string). true: the LONGER one, for batches whose every string fits the registers (W covers the longest
 // string of the batch — config 1's words): the columns are then the shorter string's symbols, and a column costs the same
 // whatever the pattern length, so a pair of lengths (la, lb) costs min(la, lb) column steps instead of max(la, lb).
+// One pair; returns true when the pair was SKIPPED (malformed offsets, a pattern that does not fit W words, a string longer
+// than n_cap). m_out / n_out: the pair's shorter / longer length when it was not skipped.
 template <int W, bool LONG_PAT>
-__global__ void __launch_bounds__(SHORT_THREADS) lev_short_kernel(PairSpace ps, uint64_t begin, uint64_t count, uint32_t n_cap) {
-    const uint64_t local = (uint64_t)blockIdx.x * SHORT_THREADS + threadIdx.x;
-    if (local >= count) return;
-    const uint32_t opaque0 = (uint32_t)(count >> 63); // run-time 0: see mad_lo in lev_bitpar.cuh
+__device__ __forceinline__ bool lev_short_pair(const PairSpace &ps, uint64_t slot, uint32_t n_cap, uint32_t opaque0, uint32_t &m_out, uint32_t &n_out) {
     const ShortConsts k{1u + opaque0, 2u + opaque0, 0x01010101u + opaque0, 256u + opaque0, 65536u + opaque0};
-    const PairView pv = pair_at(ps, begin + local);
+    const PairRequest rq = pair_request(ps, slot);
+    if (!request_ok(rq)) return true;
+    const PairView pv = pair_resolve(ps, rq);
     const bool swap = LONG_PAT ? pv.la < pv.lb : pv.la > pv.lb;
     const uint8_t *pat_p = swap ? pv.b : pv.a;
     const uint8_t *txt_p = swap ? pv.a : pv.b;
     const uint32_t m = swap ? pv.lb : pv.la;
     const uint32_t n = swap ? pv.la : pv.lb;
+    m_out = min(m, n), n_out = max(m, n);
+    if (max(m, n) > n_cap) return true; // a length the host has not seen yet (speculative launch)
     if (min(m, n) == 0) {
         store_result(ps, pv.out_index, max(m, n));
-        return;
+        return false;
     }
-    if (m > 4u * W || max(m, n) > n_cap) return; // not this kernel's class, or a length the host has not validated yet (speculative launch)
+    if (m > 4u * W) return true; // not this kernel's class
 
     // pattern: up to two 16-byte pieces, re-aligned in registers to start at its first byte
     PieceStream pat_stream, txt_stream;
@@ -133,6 +136,17 @@ __global__ void __launch_bounds__(SHORT_THREADS) lev_short_kernel(PairSpace ps, 
     }
     const uint32_t rows = ((1u << m) - 1u) << 7; // the pattern's rows (m <= 24)
     store_result(ps, pv.out_index, (int64_t)n + __popc(Pv & rows) - __popc(Mv & rows));
+    return false;
+}
+
+template <int W, bool LONG_PAT>
+__global__ void __launch_bounds__(SHORT_THREADS) lev_short_kernel(PairSpace ps, uint64_t begin, uint64_t count, uint32_t n_cap, SpecArgs sa) {
+    const uint64_t local = (uint64_t)blockIdx.x * SHORT_THREADS + threadIdx.x;
+    const uint32_t opaque0 = (uint32_t)(count >> 63); // run-time 0: see mad_lo in lev_bitpar.cuh
+    bool miss = false;
+    uint32_t m = 0, n = 0;
+    if (local < count) miss = lev_short_pair<W, LONG_PAT>(ps, begin + local, n_cap, opaque0, m, n);
+    spec_finish(sa, miss, local < count && !miss, m, n);
 }
 
 } // namespace swb

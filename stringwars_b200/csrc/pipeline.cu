@@ -151,6 +151,55 @@ static int spec_kernel_of(const Plan &plan) {
     return 0;
 }
 
+// A self-validating speculative launch (common.cuh, spec_finish): arm the report, and wait for what the kernel's last
+// block publishes. The wait spins on one mapped word and checks the stream now and then for a failed launch.
+static SpecArgs arm_spec(DeviceCtx &ctx) {
+    ctx.spec_seq++;
+    if (ctx.spec_seq == 0) ctx.spec_seq = 1;
+    SpecArgs sa;
+    sa.report = ctx.d_spec, sa.published = ctx.h_spec_dev, sa.seq = ctx.spec_seq;
+    return sa;
+}
+static swb_status_t wait_spec(DeviceCtx &ctx, cudaStream_t stream, const char **err) {
+    volatile uint32_t *seq = &ctx.h_spec->seq;
+    for (uint64_t spins = 0; *seq != ctx.spec_seq; ++spins) {
+        if ((spins & 0x3FFF) == 0x3FFF) {
+            cudaError_t q = cudaStreamQuery(stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) return fail(err, SWB_CUDA_ERROR, "speculative kernel failed: %s", cudaGetErrorString(q));
+            if (q == cudaSuccess && *seq != ctx.spec_seq && spins > (1ull << 26)) return fail(err, SWB_CUDA_ERROR, "speculative kernel never reported");
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return SWB_OK;
+}
+
+// The kernel a uniform byte-Levenshtein batch of these extrema would get from the regular path (launch_lev_bitpar's code),
+// 0 when the batch is not uniform enough to be worth a bet (one pattern class, text lengths within two 32-byte bins).
+static int spec_kernel_for(uint32_t min_m, uint32_t max_m, uint32_t min_n, uint32_t max_n) {
+    auto cls = [](uint32_t m) { return m <= 32 ? 0 : (m <= 64 ? 1 : (m <= 128 ? 2 : (m <= 256 ? 3 : 4))); };
+    if (max_m > 256 || cls(std::max(min_m, 1u)) != cls(std::max(max_m, 1u))) return 0;
+    if ((max_n + 31u) / 32u > (min_n + 31u) / 32u + 1u) return 0;
+    if (max_n <= 8) return -12;
+    if (max_n <= 16) return -14;
+    if (max_n <= 24) return -16;
+    if (max_m <= 8) return -2;
+    if (max_m <= 16) return -4;
+    if (max_m <= 24) return -6;
+    if (max_m <= 32) return 1;
+    if (max_m <= 64) return 2;
+    if (max_m <= 128) return 4;
+    return 8;
+}
+
+// Batches up to this many pairs bet with ONE self-validating launch and wait for its report (the call is latency-bound:
+// a second launch and a statistics pass would be most of it). Larger batches bet with the kernel on the caller's stream
+// and the statistics kernel beside it on a side stream, and return as soon as the statistics are in — the compute kernel
+// keeps running, so consecutive calls (and the devices of a multi-device scope) overlap.
+constexpr uint64_t SPEC_SINGLE_LAUNCH_PAIRS = 1u << 17;
+
 swb_status_t swb::run_device_batch(swb_engine *eng, int dev_index, PairSpace ps, cudaStream_t stream, const char **err) {
     DeviceCtx &ctx = eng->scope->devs[dev_index];
     if (ps.n_pairs == 0) return SWB_OK;
@@ -180,7 +229,7 @@ swb_status_t swb::run_device_batch(swb_engine *eng, int dev_index, PairSpace ps,
         if (spec_q) {
             SWB_CUDA(cudaEventRecord(ctx.ev_inputs, stream));
             SWB_CUDA(cudaStreamWaitEvent(ctx.side_stream, ctx.ev_inputs, 0));
-            if ((st = launch_lev_cross(eng, ctx, ps, (uint32_t)n_q, (uint32_t)cpb, spec_q, spec_n, stream, err)) != SWB_OK) return st;
+            if ((st = launch_lev_cross(eng, ctx, ps, (uint32_t)n_q, (uint32_t)cpb, spec_q, spec_n, SpecArgs{}, stream, err)) != SWB_OK) return st;
             if ((st = enqueue_schedule_count(ctx, qs, ctx.side_stream, err, ps.b_offs, ps.n_c, (ps.offs32 >> 1) & 1u)) != SWB_OK) return st;
         } else if ((st = enqueue_schedule_count(ctx, qs, stream, err, ps.b_offs, ps.n_c, (ps.offs32 >> 1) & 1u)) != SWB_OK) {
             return st;
@@ -191,28 +240,42 @@ swb_status_t swb::run_device_batch(swb_engine *eng, int dev_index, PairSpace ps,
         uint32_t max_q = 0;
         for (int c = 0; c < SCHED_MCLASSES; ++c) max_q = std::max(max_q, ctx.h_stats->max_m[c]);
         const uint32_t max_c = ctx.h_stats->extra_max;
-        const bool worth = max_q <= 256;
         auto words_of = [](uint32_t q) { return q <= 32 ? 1 : (q <= 64 ? 2 : (q <= 128 ? 4 : 8)); };
-        if (worth) {
+        if (max_q <= 256) {
             eng->spec_cross_q = std::max(max_q, 1u), eng->spec_cross_n = max_c;
             if (spec_q && words_of(max_q) == words_of(spec_q) && max_c <= spec_n) return SWB_OK; // the bet held
-            return launch_lev_cross(eng, ctx, ps, (uint32_t)n_q, (uint32_t)cpb, max_q, 0xFFFFFFFFu, stream, err);
+            return launch_lev_cross(eng, ctx, ps, (uint32_t)n_q, (uint32_t)cpb, max_q, 0xFFFFFFFFu, SpecArgs{}, stream, err);
         }
     }
-    // Speculate that this batch has the shape of the previous one. A thread-per-pair bit-vector kernel is correct
-    // for every pair that fits its K words and skips the others, and its launch geometry depends on nothing but
-    // the pair count, so it goes onto the caller's stream IMMEDIATELY while the schedule kernel runs beside it on
-    // a side stream: the host round trip and the schedule kernel leave the critical path. If the counters then
-    // show a different shape, the batch is simply processed again the regular way (results overwritten in order).
+    // Element-wise pairs (and cross products too small for the cross kernel): bet that this batch has the shape of the
+    // previous one. A thread-per-pair kernel is correct for every pair that fits its words and skips the others (malformed
+    // offsets and strings longer than the previous batch's longest included), and its launch geometry depends on nothing
+    // but the pair count, so it goes onto the caller's stream IMMEDIATELY.
     const int spec = (lev_bytes && eng->algorithm != SWB_ALGO_WAVEFRONT) ? eng->spec_class : 0;
-    if (spec != 0) {
+    bool have_stats = false;
+    if (spec != 0 && ps.n_pairs <= SPEC_SINGLE_LAUNCH_PAIRS) {
+        // small batch: the kernel validates as it goes and its last block reports misses and the batch's length extrema
+        eng->spec_class = 0;
+        const SpecArgs sa = arm_spec(ctx);
+        if ((st = launch_lev_bitpar(eng, ctx, spec, ps, 0, ps.n_pairs, eng->spec_max_n, sa, stream, err)) != SWB_OK) return st;
+        if ((st = wait_spec(ctx, stream, err)) != SWB_OK) return st;
+        const SpecPublished &r = *ctx.h_spec;
+        if (r.misses == 0) { // that kernel was the batch; the extrema decide the next bet (same kernel, a narrower one, or none)
+            eng->spec_class = r.max_n ? spec_kernel_for(r.min_m, r.max_m, r.min_n, r.max_n) : spec;
+            if (r.max_n) eng->spec_max_n = r.max_n;
+            return SWB_OK;
+        }
+    } else if (spec != 0) {
+        // large batch: the statistics kernel runs beside the bet on a side stream; the host returns when the statistics are in
         SWB_CUDA(cudaEventRecord(ctx.ev_inputs, stream));
         SWB_CUDA(cudaStreamWaitEvent(ctx.side_stream, ctx.ev_inputs, 0));
-        if ((st = launch_lev_bitpar(eng, ctx, spec, ps, 0, ps.n_pairs, eng->spec_max_n, stream, err)) != SWB_OK) return st;
+        if ((st = launch_lev_bitpar(eng, ctx, spec, ps, 0, ps.n_pairs, eng->spec_max_n, SpecArgs{}, stream, err)) != SWB_OK) return st;
         if ((st = enqueue_schedule_count(ctx, ps, ctx.side_stream, err)) != SWB_OK) return st;
-    } else if ((st = enqueue_schedule_count(ctx, ps, stream, err)) != SWB_OK) {
-        return st;
+        have_stats = true;
     }
+    // The regular way: statistics pass (also where malformed offsets become SWB_INVALID_ARG), bucketing, per-class kernels;
+    // after a lost bet the results are simply overwritten in order.
+    if (!have_stats && (st = enqueue_schedule_count(ctx, ps, stream, err)) != SWB_OK) return st;
     if ((st = wait_schedule_count(ctx, err)) != SWB_OK) return st;
     eng->spec_class = 0;
     if ((st = refuse_bad_offsets(ctx, err)) != SWB_OK) return st;
@@ -221,7 +284,7 @@ swb_status_t swb::run_device_batch(swb_engine *eng, int dev_index, PairSpace ps,
     const int kernel_now = (uniform && lev_bytes) ? spec_kernel_of(plan) : 0;
     const uint32_t spec_cap = eng->spec_max_n;
     eng->spec_class = kernel_now, eng->spec_max_n = plan.n_classes ? plan.max_n[0] : 0u;
-    if (spec != 0 && kernel_now == spec && eng->spec_max_n <= spec_cap) return SWB_OK; // the bet held: that kernel is the batch
+    if (have_stats && kernel_now == spec && eng->spec_max_n <= spec_cap) return SWB_OK; // the bet held: that kernel is the batch
     if (!plan.identity && (st = enqueue_scatter(ctx, ps, stream, err)) != SWB_OK) return st;
     for (int i = 0; i < plan.n_classes; ++i) {
         st = launch_class(eng, ctx, dev_index, ps, plan.begin[i], plan.count[i], plan.max_m[i], plan.max_n[i], stream, err, plan.same_shape);
