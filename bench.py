@@ -339,6 +339,24 @@ def run_gates(bench, sw, datasets, scope, engine, args, peak, host_threads):
         harness[name] = entry
     gates["harness_shape"] = harness
 
+    # ---- the compiled twin of the reference's bench.rs block (harness/bench_similarities.cpp): the same call from C++, without
+    # this script's ctypes overhead per call — what a Rust harness would see. Synthetic words, managed tape and matrix.
+    twin = os.path.join(ROOT, "harness", "bench_similarities")
+    if os.path.exists(twin):
+        rows = {}
+        for label, per_core in (("default_256_per_sm", "256"), ("published_16384_per_sm", "16384")):
+            env = dict(os.environ, STRINGWARS_TIME="0.5", STRINGWARS_WARMUP="0.2", STRINGWARS_FILTER="levenshtein<1gpu>", STRINGWARS_BATCH_PER_CORE=per_core)
+            try:
+                out = subprocess.run([twin], env=env, capture_output=True, text=True, timeout=120).stdout
+                for ln in out.splitlines():
+                    if ln.startswith("uniform/stringwars_b200::levenshtein<1gpu>"):
+                        parts = ln.split()
+                        scale = {"T": 1e3, "G": 1.0, "M": 1e-3, "k": 1e-6}[parts[2][0]] if parts[2][0] in "TGMk" else 1e-9
+                        rows[label] = {"gcups": float(parts[1]) * scale, "p50_us": float(ln.split("p50")[1].split("us")[0]), "line": ln.strip()}
+            except Exception as exc:
+                rows[label] = {"error": str(exc)}
+        harness["words_cpp_twin"] = rows
+
     # ---- config 3 (UTF-8 lines, byte and code-point engines) and config 5 (NW, 10k x 1024)
     la, lb = datasets.utf8_line_pairs(100_000, seed=3)
     l_cells = float((la.lengths().astype(np.float64) * lb.lengths().astype(np.float64)).sum())

@@ -810,6 +810,8 @@ static swb_status_t host_cross(swb_engine *engine, const Side &Q, const Side &C,
     swb_scope *scope = engine->scope;
     const int D = (int)scope->devs.size();
     const size_t elt = result_bytes(out_narrow);
+    const double t_begin = trace_enabled() ? now_ms() : 0;
+    double t_placed = 0, t_launched = 0;
     const PtrInfo out_mem = classify(out);
     const int forced = forced_device(scope, {Q.tape ? PtrInfo{} : Q.data_mem, Q.tape ? PtrInfo{} : Q.offs_mem, C.tape ? PtrInfo{} : C.data_mem,
                                              C.tape ? PtrInfo{} : C.offs_mem, out_mem});
@@ -841,6 +843,7 @@ static swb_status_t host_cross(swb_engine *engine, const Side &Q, const Side &C,
         }
         PairSpace ps = make_pair_space(q.data_biased, q.offs_at_lo, c.data_biased, c.offs_at_lo, (q_hi - q_lo) * n_c, n_c, stride, d_out, out_narrow,
                                        Q.bit32() | (C.bit32() << 1));
+        if (trace_enabled()) t_placed = now_ms();
         if (engine->kind == ENGINE_LEVENSHTEIN_UTF8) {
             uint64_t q_bytes = q.hi_off - q.lo_off, c_bytes = c.hi_off - c.lo_off;
             if (!Q.host_offsets() && (st = device_span(q.offs_at_lo, Q.width, q_hi - q_lo, ctx.compute_stream, &q_bytes, err)) != SWB_OK) return st;
@@ -853,10 +856,14 @@ static swb_status_t host_cross(swb_engine *engine, const Side &Q, const Side &C,
             SWB_CUDA(cudaMemcpy2DAsync((uint8_t *)out + q_lo * row_stride * elt, row_stride * elt, ctx.out.ptr, n_c * elt, n_c * elt, q_hi - q_lo,
                                        cudaMemcpyDeviceToHost, ctx.compute_stream));
     }
+    if (trace_enabled()) t_launched = now_ms();
     for (int d = 0; d < D; ++d) {
         SWB_CUDA(cudaSetDevice(scope->devs[d].device));
         SWB_CUDA(cudaStreamSynchronize(scope->devs[d].compute_stream));
     }
+    if (trace_enabled())
+        fprintf(stderr, "[swb trace] cross %llu x %llu: classify+place=%.1f us run=%.1f us sync=%.1f us total=%.1f us\n", (unsigned long long)n_q,
+                (unsigned long long)n_c, (t_placed - t_begin) * 1e3, (t_launched - t_placed) * 1e3, (now_ms() - t_launched) * 1e3, (now_ms() - t_begin) * 1e3);
     return SWB_OK;
 }
 
