@@ -141,6 +141,7 @@ extern "C" swb_status_t swb_scope_create_devices(const int *devices, int num_dev
         cudaError_t e = cudaSetDevice(c.device);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, c.device);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c.concurrent_managed, cudaDevAttrConcurrentManagedAccess, c.device);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c.compute_stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) {

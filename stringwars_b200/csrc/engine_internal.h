@@ -79,6 +79,7 @@ struct DeviceCtx {
     int device = 0;
     int sm_count = 0;
     int max_smem_optin = 0;
+    int concurrent_managed = 0; // the host may touch managed memory without synchronising the device first
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
     cudaStream_t side_stream = nullptr; // schedule kernel of speculative device-resident calls
     cudaEvent_t ev_inputs = nullptr;    // "caller's stream has reached this call": inputs are ready
@@ -191,7 +192,9 @@ static inline uint32_t round16(uint32_t x) { return (x + 15u) & ~15u; }
 
 // ------------------------------------------------------------------------------------------ pipeline.cu
 // Run a fully device-resident PairSpace on scope device `dev_index`: schedule, (scatter), per-class kernels.
-swb_status_t run_device_batch(swb_engine *eng, int dev_index, PairSpace ps, cudaStream_t stream, const char **err);
+// `completed` (optional) is set when the call has already SEEN the batch finish (a self-validating launch whose report
+// arrived): results are written and visible device-wide, no stream synchronisation is needed to know it.
+swb_status_t run_device_batch(swb_engine *eng, int dev_index, PairSpace ps, cudaStream_t stream, const char **err, bool *completed = nullptr);
 // Same for the code-point engine (decodes both tapes first). n_a / n_b: strings per tape; *_bytes: their byte spans.
 swb_status_t run_device_batch_utf8(swb_engine *eng, int dev_index, PairSpace ps, uint64_t n_a, uint64_t n_b, uint64_t a_bytes,
                                    uint64_t b_bytes, cudaStream_t stream, const char **err);

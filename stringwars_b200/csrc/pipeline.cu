@@ -200,8 +200,9 @@ static int spec_kernel_for(uint32_t min_m, uint32_t max_m, uint32_t min_n, uint3
 // keeps running, so consecutive calls (and the devices of a multi-device scope) overlap.
 constexpr uint64_t SPEC_SINGLE_LAUNCH_PAIRS = 1u << 17;
 
-swb_status_t swb::run_device_batch(swb_engine *eng, int dev_index, PairSpace ps, cudaStream_t stream, const char **err) {
+swb_status_t swb::run_device_batch(swb_engine *eng, int dev_index, PairSpace ps, cudaStream_t stream, const char **err, bool *completed) {
     DeviceCtx &ctx = eng->scope->devs[dev_index];
+    if (completed) *completed = false;
     if (ps.n_pairs == 0) return SWB_OK;
     if (ps.n_pairs >= 0xFFFFFFFFull) return fail(err, SWB_INVALID_ARG, "more than 2^32-1 pairs in one call");
     ps.order = nullptr;
@@ -263,6 +264,7 @@ swb_status_t swb::run_device_batch(swb_engine *eng, int dev_index, PairSpace ps,
         if (r.misses == 0) { // that kernel was the batch; the extrema decide the next bet (same kernel, a narrower one, or none)
             eng->spec_class = r.max_n ? spec_kernel_for(r.min_m, r.max_m, r.min_n, r.max_n) : spec;
             if (r.max_n) eng->spec_max_n = r.max_n;
+            if (completed) *completed = true;
             return SWB_OK;
         }
     } else if (spec != 0) {
@@ -295,19 +297,23 @@ swb_status_t swb::run_device_batch(swb_engine *eng, int dev_index, PairSpace ps,
 
 // ------------------------------------------------------------------------------------------ UTF-8 engine
 
-// Symbol offsets of one device byte tape (count -> scan): sym_offs[i] = 4 x (symbols before string i). `offs` points at
-// n+1 offsets (u64, or u32 when offs32) valid with `data` (biased pointers are fine).
+// Symbol counts of one device byte tape: sym_offs[i + 1] = 4 x (symbols of string i), and the ASCII flag is cleared when a
+// byte >= 0x80 is seen. `offs` points at n+1 offsets (u64, or u32 when offs32) valid with `data` (biased pointers are fine).
 static swb_status_t count_symbols(DeviceCtx &ctx, const uint8_t *data, const void *offs, uint32_t offs32, uint64_t n, DeviceBuffer &sym_offs,
                                   uint32_t *d_ascii_flag, cudaStream_t stream, const char **err) {
     SWB_CUDA(sym_offs.reserve((n + 1) * sizeof(uint64_t)));
+    const unsigned blocks = (unsigned)((n * 32 + 255) / 256);
+    utf8_count_kernel<<<blocks, 256, 0, stream>>>(data, offs, offs32, n, (uint64_t *)sym_offs.ptr, d_ascii_flag);
+    g_launches++;
+    SWB_CUDA(cudaGetLastError());
+    return SWB_OK;
+}
+// Counts -> offsets (inclusive scan in place): sym_offs[i] = 4 x (symbols before string i).
+static swb_status_t scan_symbols(DeviceCtx &ctx, uint64_t n, DeviceBuffer &sym_offs, cudaStream_t stream, const char **err) {
     size_t tmp_bytes = 0;
     uint64_t *so = (uint64_t *)sym_offs.ptr;
     SWB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, so, so, (int)(n + 1), stream));
     SWB_CUDA(ctx.scan_tmp.reserve(tmp_bytes + 16));
-    const unsigned blocks = (unsigned)((n * 32 + 255) / 256);
-    utf8_count_kernel<<<blocks, 256, 0, stream>>>(data, offs, offs32, n, so, d_ascii_flag);
-    g_launches++;
-    SWB_CUDA(cudaGetLastError());
     SWB_CUDA(cub::DeviceScan::InclusiveSum(ctx.scan_tmp.ptr, tmp_bytes, so, so, (int)(n + 1), stream));
     return SWB_OK;
 }
@@ -367,6 +373,8 @@ swb_status_t swb::run_device_batch_utf8(swb_engine *eng, int dev_index, PairSpac
     SWB_CUDA(cudaMemcpyAsync(&h_ascii, d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     SWB_CUDA(cudaStreamSynchronize(stream));
     if (h_ascii != 0) return run_device_batch(eng, dev_index, ps, stream, err);
+    if ((st = scan_symbols(ctx, n_a, ctx.sym_a_offs, stream, err)) != SWB_OK) return st;
+    if (!same_tape && (st = scan_symbols(ctx, n_b, ctx.sym_b_offs, stream, err)) != SWB_OK) return st;
     if ((st = pack_symbols(ctx, ps.a_data, ps.a_offs, a32, n_a, a_bytes, ctx.sym_a, ctx.sym_a_offs, stream, err)) != SWB_OK) return st;
     if (!same_tape && (st = pack_symbols(ctx, ps.b_data, ps.b_offs, b32, n_b, b_bytes, ctx.sym_b, ctx.sym_b_offs, stream, err)) != SWB_OK) return st;
     PairSpace sym = ps;
@@ -818,6 +826,8 @@ static swb_status_t host_cross(swb_engine *engine, const Side &Q, const Side &C,
     if (forced == -2) return fail(err, SWB_INVALID_ARG, "device pointers must all belong to one device of the scope");
     const bool staged_out = out_mem.kind == MEM_HOST;
     swb_status_t st;
+    bool seen_done[64] = {false};
+    if (D > 64) return fail(err, SWB_INVALID_ARG, "scopes of more than 64 devices are not supported");
     for (int d = 0; d < D; ++d) {
         DeviceCtx &ctx = scope->devs[d];
         uint64_t q_lo = n_q * d / D, q_hi = n_q * (d + 1) / D;
@@ -849,7 +859,7 @@ static swb_status_t host_cross(swb_engine *engine, const Side &Q, const Side &C,
             if (!Q.host_offsets() && (st = device_span(q.offs_at_lo, Q.width, q_hi - q_lo, ctx.compute_stream, &q_bytes, err)) != SWB_OK) return st;
             if (!C.host_offsets() && (st = device_span(c.offs_at_lo, C.width, n_c, ctx.compute_stream, &c_bytes, err)) != SWB_OK) return st;
             if ((st = run_device_batch_utf8(engine, d, ps, q_hi - q_lo, n_c, q_bytes, c_bytes, ctx.compute_stream, err)) != SWB_OK) return drain(scope), st;
-        } else if ((st = run_device_batch(engine, d, ps, ctx.compute_stream, err)) != SWB_OK) {
+        } else if ((st = run_device_batch(engine, d, ps, ctx.compute_stream, err, &seen_done[d])) != SWB_OK) {
             return drain(scope), st;
         }
         if (staged_out)
@@ -858,6 +868,8 @@ static swb_status_t host_cross(swb_engine *engine, const Side &Q, const Side &C,
     }
     if (trace_enabled()) t_launched = now_ms();
     for (int d = 0; d < D; ++d) {
+        // results written in place by a kernel whose completion report has been read are final and visible: no synchronisation
+        if (seen_done[d] && !staged_out && (out_mem.kind == MEM_DEVICE || scope->devs[d].concurrent_managed)) continue;
         SWB_CUDA(cudaSetDevice(scope->devs[d].device));
         SWB_CUDA(cudaStreamSynchronize(scope->devs[d].compute_stream));
     }
