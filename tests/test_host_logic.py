@@ -51,3 +51,41 @@ def test_budget_from_env(monkeypatch):
     monkeypatch.setenv("STRINGWARS_WARMUP", "0")
     b = harness.BenchBudget.from_env(5.0, 30.0)
     assert b.time_seconds == 1.5 and b.warmup_seconds == 0.0
+
+
+def test_tapes_with_u32_offsets_and_views():
+    """`BytesTapeView<u32>` / `AnyBytesTape::View32`: offsets keep their width through subviews and into the C view."""
+    import pytest
+    t = BytesTape.from_strings([b"kitten", b"", b"sitting", "naïve"], offset_dtype=np.uint32)
+    assert t.offsets.dtype == np.uint32 and t.offset_bits == 32 and len(t) == 4
+    assert t[2] == b"sitting" and t[3] == "naïve".encode() and t.lengths().tolist() == [6, 0, 7, 6]
+    sub = t.subview(1, 3)
+    assert sub.offsets.dtype == np.uint32 and len(sub) == 2 and sub[1] == b"sitting" and int(sub.offsets[0]) == 6  # offsets stay absolute
+    v = sub.view()
+    assert v.n == 2 and v.offset_bits == 32 and v.data == t.data.ctypes.data and v.offsets == sub.offsets.ctypes.data
+    wide = t.with_offsets(np.uint64)
+    assert wide.offset_bits == 64 and wide[3] == t[3] and wide.view().offset_bits == 64
+    assert BytesTape(np.zeros(4, np.uint8), [0, 2, 4]).offsets.dtype == np.uint64  # anything else is widened to u64
+    with pytest.raises(IndexError):
+        t.subview(2, 9)
+    empty = BytesTape.from_strings([])
+    assert len(empty) == 0 and empty.view().n == 0 and empty.view().data != 0  # never a NULL data pointer
+
+
+def test_result_width_checks_need_no_gpu():
+    """`swb_result_type_t`: the Python mirror accepts 64 / 32 / 16-bit results of the engine's signedness only."""
+    import pytest
+    from stringwars_b200 import _lib, szs
+    assert szs._check_out(np.zeros(5, np.uint16), np.uint64, 5) == _lib.RESULT_16
+    assert szs._check_out(np.zeros(5, np.uint32), np.uint64, 5) == _lib.RESULT_32
+    assert szs._check_out(np.zeros(5, np.int64), np.int64, 5) == _lib.RESULT_64
+    for bad in (np.zeros(5, np.int16), np.zeros(4, np.uint16), np.zeros(5, np.uint8), np.zeros((5, 2), np.uint64)[:, 0]):
+        with pytest.raises(ValueError):
+            szs._check_out(bad, np.uint64, 5)
+
+
+def test_bench_config_object_is_shared_by_both_arms():
+    import bench
+    length, pairs, name = bench.WORKLOADS["ascii64"]
+    cfg = bench.shared_config("ascii64", name, pairs, length)
+    assert cfg["pairs_per_gpu"] == 1 << 20 and cfg["length"] == 64 and "configs[1]" in cfg["workload"] and "L2" in cfg["l2"]
