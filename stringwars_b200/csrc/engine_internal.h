@@ -211,8 +211,10 @@ swb_status_t check_engine_alive(swb_engine *engine, const char **err);
 
 // ------------------------------------------------------------------------------------------ launchers
 // launch_lev.cu: one length class of byte Levenshtein by the bit-vector kernels (any pattern length).
+// min_m: the class's shortest pattern when the caller knows it (0: unknown) — a class whose every pattern fills its K words
+// exactly can take the software-pipelined kernel
 swb_status_t launch_lev_class(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count, uint32_t max_m,
-                              uint32_t max_n, cudaStream_t stream, const char **err);
+                              uint32_t max_n, cudaStream_t stream, const char **err, uint32_t min_m = 0);
 // thread-per-pair kernel of word count K = 1, 2, 4, 8 (or the register kernel of -K pattern words) over the whole pair
 // space — the speculative launch: pairs that are malformed, do not fit, or whose longer string exceeds n_cap are skipped and
 // reported through `sa`

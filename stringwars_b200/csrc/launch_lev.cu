@@ -11,6 +11,7 @@
 #ifdef SWB_EXPERIMENTS
 #include "lev_bitpar_ws.cuh"
 #endif
+#include "lev_bitpar_pipe.cuh"
 #include "lev_short.cuh"
 
 namespace swb {
@@ -58,6 +59,30 @@ static swb_status_t launch_bitpar(swb_engine *eng, DeviceCtx &ctx, const PairSpa
     g_launches++;
     static const char *names[] = {"", "lev_bitpar<K=1>", "lev_bitpar<K=2>", "", "lev_bitpar<K=4>", "", "", "", "lev_bitpar<K=8>"};
     eng->last_kernel = names[K];
+    SWB_CUDA(cudaGetLastError());
+    return SWB_OK;
+}
+
+// Software-pipelined form of the thread-per-pair kernel (lev_bitpar_pipe.cuh) for batches whose every pattern has exactly
+// 32 K symbols: persistent threads, two table buffers each, the next pair's tables built inside the current pair's columns.
+constexpr int PIPE_BLOCKS_PER_SM = 6;     // 32 KB of tables per block
+constexpr uint64_t PIPE_MIN_PAIRS_PER_THREAD = 6; // below that the un-overlapped first build is not amortised
+template <int K>
+static bool pipe_worth(const DeviceCtx &ctx, uint64_t count) {
+    return count >= (uint64_t)ctx.sm_count * PIPE_BLOCKS_PER_SM * PipeConfig<K>::THREADS * PIPE_MIN_PAIRS_PER_THREAD;
+}
+template <int K>
+static swb_status_t launch_bitpar_pipe(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count, cudaStream_t stream,
+                                       const char **err, uint32_t n_cap) {
+    const size_t smem = PipeConfig<K>::SMEM;
+    SWB_CUDA(allow_smem((const void *)lev_bitpar_pipe_kernel<K>, ctx.device, smem));
+    const unsigned blocks = (unsigned)std::min<uint64_t>((count + PipeConfig<K>::THREADS - 1) / PipeConfig<K>::THREADS, (uint64_t)ctx.sm_count * PIPE_BLOCKS_PER_SM);
+    {
+        ProfileBracket bracket(eng, ctx.device, stream);
+        lev_bitpar_pipe_kernel<K><<<blocks, PipeConfig<K>::THREADS, smem, stream>>>(ps, begin, count, n_cap);
+    }
+    g_launches++;
+    eng->last_kernel = "lev_bitpar_pipe<K=2>";
     SWB_CUDA(cudaGetLastError());
     return SWB_OK;
 }
@@ -139,6 +164,9 @@ swb_status_t launch_lev_bitpar(swb_engine *eng, DeviceCtx &ctx, int K, const Pai
     case -2: return launch_short<2>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
     case -4: return launch_short<4>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
     case -6: return launch_short<6>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
+    case 102: // every pattern exactly 64 symbols: the pipelined kernel when the batch is large enough to amortise its prologue
+        if (pipe_worth<2>(ctx, count) && !sa.report) return launch_bitpar_pipe<2>(eng, ctx, ps, begin, count, stream, err, n_cap);
+        return launch_bitpar<2>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
     case 1: return launch_bitpar<1>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
     case 2: return launch_bitpar<2>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
     case 4: return launch_bitpar<4>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
@@ -156,7 +184,7 @@ swb_status_t launch_lev_cross(swb_engine *eng, DeviceCtx &ctx, const PairSpace &
 }
 
 swb_status_t launch_lev_class(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count, uint32_t max_m,
-                              uint32_t max_n, cudaStream_t stream, const char **err) {
+                              uint32_t max_n, cudaStream_t stream, const char **err, uint32_t min_m) {
 #ifdef SWB_EXPERIMENTS
     // SWB_EXP (bit mask, experiments only): 1: <=256 B via lane groups <4,2>; 2: <=1024 B via <8,4>; 4: <=512 B via <4,4>;
     // 8: patterns <= 32 B through the table kernel (K = 1) instead of the register kernel
@@ -174,6 +202,7 @@ swb_status_t launch_lev_class(swb_engine *eng, DeviceCtx &ctx, const PairSpace &
     if (max_m <= 16) return launch_short<4>(eng, ctx, ps, begin, count, stream, err);
     if (max_m <= SHORT_MAX_M) return launch_short<6>(eng, ctx, ps, begin, count, stream, err);
     if (max_m <= 32) return launch_bitpar<1>(eng, ctx, ps, begin, count, stream, err);
+    if (max_m == 64 && min_m == 64 && pipe_worth<2>(ctx, count)) return launch_bitpar_pipe<2>(eng, ctx, ps, begin, count, stream, err, 0xFFFFFFFFu);
     if (max_m <= 64) return launch_bitpar<2>(eng, ctx, ps, begin, count, stream, err);
     if (max_m <= 128) return launch_bitpar<4>(eng, ctx, ps, begin, count, stream, err);
     if (max_m <= 256) return launch_bitpar<8>(eng, ctx, ps, begin, count, stream, err);

@@ -39,7 +39,8 @@ static swb_status_t launch_class(swb_engine *eng, DeviceCtx &ctx, int dev_index,
                                  uint64_t count, uint32_t max_m, uint32_t max_n, cudaStream_t stream, const char **err, bool same_shape = false) {
     if (count == 0) return SWB_OK;
     const bool lev = eng->kind == ENGINE_LEVENSHTEIN || eng->kind == ENGINE_LEVENSHTEIN_UTF8;
-    if (lev && ps.len_shift == 0 && eng->algorithm != SWB_ALGO_WAVEFRONT) return launch_lev_class(eng, ctx, ps, begin, count, max_m, max_n, stream, err);
+    if (lev && ps.len_shift == 0 && eng->algorithm != SWB_ALGO_WAVEFRONT)
+        return launch_lev_class(eng, ctx, ps, begin, count, max_m, max_n, stream, err, same_shape ? max_m : 0u);
     return launch_wavefront(eng, ctx, dev_index, ps, begin, count, max_m, max_n, stream, err, same_shape);
 }
 
@@ -138,6 +139,7 @@ static swb_status_t enqueue_scatter(DeviceCtx &ctx, PairSpace &ps, cudaStream_t 
 // pair count. Classes 0..3 are the table kernels of 1, 2, 4, 8 words; short patterns use the register kernels.
 static int spec_kernel_of(const Plan &plan) {
     const uint32_t m = plan.max_m[0], n = plan.max_n[0];
+    if (plan.same_shape && m == 64) return 102; // every pattern fills two words exactly: the software-pipelined kernel
     if (n <= 8) return -12;
     if (n <= 16) return -14;
     if (n <= 24) return -16;

@@ -442,3 +442,49 @@ def test_codepoint_engine_alphabet_compaction_and_its_fallback(scope, oracle):
     want = oracle.levenshtein_pairs(ta.data, ta.offsets, tb.data, tb.offsets, oracle.UTF8, threads=8)
     assert np.array_equal(utf8.compute_pairs(scope, ta, tb), want)
     assert "wavefront" in utf8.last_kernel, utf8.last_kernel
+
+
+# ------------------------------------------------------------------------------------------ software-pipelined kernel
+
+@pytest.mark.parametrize("la,lb,shift", [(64, 64, 0), (64, 100, 0), (90, 64, 3), (64, 64, 7), (64, 17 * 16, 1)])
+def test_pipelined_kernel_on_full_pattern_batches(scope, oracle, la, lb, shift):
+    """lev_bitpar_pipe<K=2>: large batches whose every shorter string has exactly 64 symbols (texts longer, either side the
+    shorter one, tapes at odd byte alignments), device-resident (first call: regular kernel; repeated calls: the bet) and
+    resident tapes through the host call."""
+    import torch
+    n = 400_003
+    rng = np.random.default_rng(la * 1000 + lb + shift)
+    alphabet = np.arange(0x20, 0x7F, dtype=np.uint8)
+    a = datasets._ragged(np.full(n, la), alphabet, rng, False)
+    b = datasets._ragged(np.full(n, lb), alphabet, rng, False)
+    # a third of the pairs nearly identical: small distances, long carry chains
+    nb = b.data.reshape(n, lb).copy()
+    k = min(la, lb)
+    nb[::3, :k] = a.data.reshape(n, la)[::3, :k]
+    nb[::3, 5] ^= 1
+    b = BytesTape.from_arrays(nb.reshape(-1), b.offsets)
+    want = _want(oracle, a, b)
+    lev = sw.LevenshteinDistances(scope)
+    dev = torch.device("cuda", 0)
+    pad = lambda x: torch.cat([torch.zeros(shift, dtype=torch.uint8), torch.from_numpy(x.copy()), torch.zeros(64, dtype=torch.uint8)]).to(dev)
+    ad, bd = pad(a.data), pad(b.data)
+    ao, bo = torch.from_numpy(a.offsets.astype(np.int64)).to(dev), torch.from_numpy(b.offsets.astype(np.int64)).to(dev)
+    out = torch.zeros(n, dtype=torch.int64, device=dev)
+    kernels = []
+    for _ in range(3):
+        out.zero_()
+        lev.compute_pairs_device(ad.data_ptr() + shift, ao.data_ptr(), bd.data_ptr() + shift, bo.data_ptr(), n, out.data_ptr())
+        torch.cuda.synchronize()
+        kernels.append(lev.last_kernel)
+        assert np.array_equal(out.cpu().numpy().astype(np.uint64), want), kernels
+    assert "lev_bitpar_pipe" in kernels[-1], kernels
+    got = lev.compute_pairs(scope, scope.upload(a), scope.upload(b))
+    assert np.array_equal(got, want) and "lev_bitpar_pipe" in lev.last_kernel
+    # a batch of another shape right after: the bet is lost, the result is not
+    a2, b2 = datasets.ascii_pairs(400_003, 48, seed=5)
+    ad2, bd2 = pad(a2.data), pad(b2.data)
+    ao2, bo2 = torch.from_numpy(a2.offsets.astype(np.int64)).to(dev), torch.from_numpy(b2.offsets.astype(np.int64)).to(dev)
+    lev.compute_pairs_device(ad.data_ptr() + shift, ao.data_ptr(), bd.data_ptr() + shift, bo.data_ptr(), n, out.data_ptr())
+    lev.compute_pairs_device(ad2.data_ptr() + shift, ao2.data_ptr(), bd2.data_ptr() + shift, bo2.data_ptr(), n, out.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().astype(np.uint64), _want(oracle, a2, b2))
