@@ -11,7 +11,9 @@
 #ifdef SWB_EXPERIMENTS
 #include "lev_bitpar_ws.cuh"
 #endif
+#ifdef SWB_EXPERIMENTS
 #include "lev_bitpar_pipe.cuh"
+#endif
 #include "lev_short.cuh"
 
 namespace swb {
@@ -63,13 +65,17 @@ static swb_status_t launch_bitpar(swb_engine *eng, DeviceCtx &ctx, const PairSpa
     return SWB_OK;
 }
 
+#ifdef SWB_EXPERIMENTS
 // Software-pipelined form of the thread-per-pair kernel (lev_bitpar_pipe.cuh) for batches whose every pattern has exactly
 // 32 K symbols: persistent threads, two table buffers each, the next pair's tables built inside the current pair's columns.
+// SWB_PIPE=1 dispatches it. Bit-exact, measured slower than lev_bitpar_kernel (30.3 vs 34.4 TCUPS at 64x64): both the ALU and
+// the shared-memory pipe are near saturation, and three warps per scheduler absorb the bursts worse than seven do.
 constexpr int PIPE_BLOCKS_PER_SM = 6;     // 32 KB of tables per block
 constexpr uint64_t PIPE_MIN_PAIRS_PER_THREAD = 6; // below that the un-overlapped first build is not amortised
 template <int K>
 static bool pipe_worth(const DeviceCtx &ctx, uint64_t count) {
-    return count >= (uint64_t)ctx.sm_count * PIPE_BLOCKS_PER_SM * PipeConfig<K>::THREADS * PIPE_MIN_PAIRS_PER_THREAD;
+    static const bool on = getenv("SWB_PIPE") != nullptr;
+    return on && count >= (uint64_t)ctx.sm_count * PIPE_BLOCKS_PER_SM * PipeConfig<K>::THREADS * PIPE_MIN_PAIRS_PER_THREAD;
 }
 template <int K>
 static swb_status_t launch_bitpar_pipe(swb_engine *eng, DeviceCtx &ctx, const PairSpace &ps, uint64_t begin, uint64_t count, cudaStream_t stream,
@@ -86,6 +92,7 @@ static swb_status_t launch_bitpar_pipe(swb_engine *eng, DeviceCtx &ctx, const Pa
     SWB_CUDA(cudaGetLastError());
     return SWB_OK;
 }
+#endif
 
 // Patterns of at most 32 bytes with the pattern's match masks derived in registers (lev_short.cuh): no tables.
 template <int W, bool LONG_PAT = false>
@@ -164,8 +171,10 @@ swb_status_t launch_lev_bitpar(swb_engine *eng, DeviceCtx &ctx, int K, const Pai
     case -2: return launch_short<2>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
     case -4: return launch_short<4>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
     case -6: return launch_short<6>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
-    case 102: // every pattern exactly 64 symbols: the pipelined kernel when the batch is large enough to amortise its prologue
+    case 102: // every pattern exactly 64 symbols (the shape the experimental pipelined kernel takes)
+#ifdef SWB_EXPERIMENTS
         if (pipe_worth<2>(ctx, count) && !sa.report) return launch_bitpar_pipe<2>(eng, ctx, ps, begin, count, stream, err, n_cap);
+#endif
         return launch_bitpar<2>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
     case 1: return launch_bitpar<1>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
     case 2: return launch_bitpar<2>(eng, ctx, ps, begin, count, stream, err, n_cap, sa);
@@ -202,7 +211,11 @@ swb_status_t launch_lev_class(swb_engine *eng, DeviceCtx &ctx, const PairSpace &
     if (max_m <= 16) return launch_short<4>(eng, ctx, ps, begin, count, stream, err);
     if (max_m <= SHORT_MAX_M) return launch_short<6>(eng, ctx, ps, begin, count, stream, err);
     if (max_m <= 32) return launch_bitpar<1>(eng, ctx, ps, begin, count, stream, err);
+#ifdef SWB_EXPERIMENTS
     if (max_m == 64 && min_m == 64 && pipe_worth<2>(ctx, count)) return launch_bitpar_pipe<2>(eng, ctx, ps, begin, count, stream, err, 0xFFFFFFFFu);
+#else
+    (void)min_m;
+#endif
     if (max_m <= 64) return launch_bitpar<2>(eng, ctx, ps, begin, count, stream, err);
     if (max_m <= 128) return launch_bitpar<4>(eng, ctx, ps, begin, count, stream, err);
     if (max_m <= 256) return launch_bitpar<8>(eng, ctx, ps, begin, count, stream, err);
