@@ -117,6 +117,16 @@ def cpu_reference(a, b, cells: float, budget_s: float, threads: int, kind=None):
     return cells * repeats / secs / 1e9, n * repeats, secs
 
 
+def cpu_model() -> str:
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def shared_config(workload: str, config_name: str, n_pairs: int, length: int):
     """The `config` object of BOTH arms (ours and --impl reference): same keys, same values."""
     return {"workload": f"{workload}: {config_name}", "pairs_per_gpu": n_pairs, "length": length,
@@ -283,7 +293,10 @@ def run_gates(bench, sw, datasets, scope, engine, args, peak, host_threads):
     one_core, _, _ = cpu_reference(sa, sb, c_small, 1.5, 1)
     bio_core, _, _ = cpu_reference(sa.subview(0, 1 << 13), sb.subview(0, 1 << 13), float(L) * L * (1 << 13), 1.5, 1, kind=orc.WAGNER_FISCHER)
     all_core, _, _ = cpu_reference(sa, sb, c_small, 1.5, host_threads)
-    gates["cpu_64x64"] = {"unit": "GCUPS", "rapidfuzz_class_1core": one_core, "bio_class_textbook_dp_1core": bio_core, f"rapidfuzz_class_{host_threads}threads": all_core,
+    bio_all, _, _ = cpu_reference(sa, sb, c_small, 1.5, host_threads, kind=orc.WAGNER_FISCHER)
+    gates["cpu_64x64"] = {"unit": "GCUPS", "cpu_model": cpu_model(), "host_threads": host_threads, "rapidfuzz_class_1core": one_core,
+                          "bio_class_textbook_dp_1core": bio_core, f"rapidfuzz_class_{host_threads}threads": all_core,
+                          f"bio_class_textbook_dp_{host_threads}threads": bio_all,
                           "note": "the reference harness times its CPU contenders on one core (bench.rs:404-459); published 1xSPR: rapidfuzz 3.3 GCUPS at 100 B, bio 0.34"}
     gates["load_phase"]["ascii64"] = load_phase(bench, engine, dev64, n, d_out, 2.0 * L * n, peak)
     del dev64
@@ -606,7 +619,7 @@ def main():
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 bit-vectors (CPU)", "data": "synthetic (seed 42, iid printable ASCII)",
             "config": config,
-            "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": host_threads, "kind": "port",
+            "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": host_threads, "kind": "port", "cpu_model": cpu_model(),
                              "sample": f"{sample} pair evaluations of {length}x{length} per step ({len(a)} distinct pairs of the workload's generator, repeated), rapidfuzz-class restatement (oracle/lev_oracle.c orc_rf_lev_bytes), {host_threads} threads"},
             "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -735,7 +748,7 @@ def main():
                 "pinned_host_u64_copies_inside": {k: {s: h[k][s]["pinned_u64"]["gcups"] for s in h["sides"]} for k in ("acgt_100", "acgt_1k", "words")},
                 "published_h100_gcups": h["published_h100_gcups"], "sides": h["sides"]}
         if cpu_gcups is not None:
-            line["cpu_baseline"] = {"value": cpu_gcups, "unit": "GCUPS", "cores": host_threads, "kind": "port",
+            line["cpu_baseline"] = {"value": cpu_gcups, "unit": "GCUPS", "cores": host_threads, "kind": "port", "cpu_model": cpu_model(),
                                     "sample": f"{cpu_sample} pair evaluations of {length}x{length} in {cpu_dt:.1f} s ({len(a0)} distinct pairs repeated), rapidfuzz-class restatement (oracle/lev_oracle.c orc_rf_lev_bytes), {host_threads} threads"}
         emit(line)
     if world > 1:
