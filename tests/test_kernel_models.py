@@ -374,3 +374,105 @@ def test_packed_range_precondition_keeps_sums_inside_int16():
         h_max = 31999 if match == 0 else min(31999, (32000 // match) * match)
         for a, b in ((floor, nxt), (h_min, first), (h_min, nxt), (h_min, mismatch), (h_max, match), (floor, first)):
             assert -32768 <= a + b <= 32767, (first, nxt, mismatch, match, a, b)
+
+
+# ------------------------------------------------------------------------------------------ round 2: lev_short.cuh, utf8.cuh
+
+def _dp4a(a, b, c=0):
+    return (sum(((a >> (8 * i)) & 0xFF) * ((b >> (8 * i)) & 0xFF) for i in range(4)) + c) & M32
+
+
+def _eq_flags(word, c):
+    """lev_short.cuh eq_flags: 0x80 in every byte of `word` equal to c — exact for all byte values (no borrow between bytes)."""
+    t = word ^ (c * 0x01010101)
+    s = ((t & 0x7F7F7F7F) + 0x7F7F7F7F) & M32
+    return ~(s | t | 0x7F7F7F7F) & M32
+
+
+def test_short_kernel_match_mask_in_registers():
+    """The register kernel derives Eq(c) without tables: SWAR zero-byte detection, two IDP.4A that pack eight flags into a
+    byte, the result positioned at bit 7 (seven free rows below the pattern). Exhaustive over all byte pairs for the
+    detector, random patterns for the packing, then whole distances against the oracle's definition."""
+    for a in range(256):
+        word = a | (((a + 1) & 0xFF) << 8) | ((a ^ 0x80) << 16) | (0x01 << 24)  # neighbours that would trip a borrowing detector
+        for c in range(256):
+            want = sum(0x80 << (8 * i) for i in range(4) if ((word >> (8 * i)) & 0xFF) == c)
+            assert _eq_flags(word, c) == want, (hex(word), c)
+    rng = random.Random(3)
+
+    def eq_mask7(pat_words, c):
+        acc = 0
+        for w in range(0, len(pat_words), 2):
+            a = _dp4a(_eq_flags(pat_words[w], c), 0x08040201)
+            if w + 1 < len(pat_words):
+                a = _dp4a(_eq_flags(pat_words[w + 1], c), 0x80402010, a)
+            acc = (acc + a * (256 ** (w // 2))) & M32
+        return acc
+
+    def short_distance(pat, txt, W):
+        data = bytes(pat) + bytes(rng.randrange(256) for _ in range(4 * W - len(pat)))  # garbage above the pattern, as in a tape
+        words = [int.from_bytes(data[4 * w: 4 * w + 4], "little") for w in range(W)]
+        Pv, Mv = [0xFFFFFF80], [0]
+        for c in txt:
+            eq = eq_mask7(words, c)
+            for i, p in enumerate(pat):  # bit 7 + i set iff pattern byte i == c
+                assert ((eq >> (7 + i)) & 1) == (p == c)
+            column_step([eq], Pv, Mv)
+        rows = ((1 << len(pat)) - 1) << 7
+        return len(txt) + bin(Pv[0] & rows).count("1") - bin(Mv[0] & rows).count("1")
+
+    for _ in range(300):
+        W = rng.choice([2, 4, 6])
+        alpha = rng.choice([2, 4, 26, 256])
+        pat = bytes(rng.randrange(alpha) for _ in range(rng.randrange(1, 4 * W + 1)))
+        txt = bytes(rng.randrange(alpha) for _ in range(rng.randrange(0, 40)))
+        assert short_distance(pat, txt, W) == pyref.levenshtein(pat, txt), (pat, txt, W)
+
+
+def test_utf8_symbol_split_and_rename_model():
+    """utf8.cuh: lead bits of a word (a byte starts a symbol iff it is not 10xxxxxx), symbols packed big-endian from a lead
+    byte and up to three continuation bytes, and the per-pair rename (dictionary of the shorter string, everything else 0)
+    preserve the code-point distance."""
+    def lead_bits4(w):
+        cont = (w >> 7) & ~(w >> 6) & 0x01010101
+        lead = cont ^ 0x01010101
+        return ((lead * 0x01020408) >> 24) & 0xF
+
+    rng = random.Random(9)
+    for _ in range(2000):
+        bs = bytes(rng.choice([0x41, 0x7F, 0x80, 0xBF, 0xC3, 0xE4, 0xF0, 0x00, 0xFF]) for _ in range(4))
+        w = int.from_bytes(bs, "little")
+        assert lead_bits4(w) == sum(1 << i for i in range(4) if (bs[i] & 0xC0) != 0x80), bs
+
+    def symbols(data):
+        out, i = [], 0
+        while i < len(data):
+            if (data[i] & 0xC0) == 0x80:  # stray continuation byte before any lead: ignored
+                i += 1
+                continue
+            sym, j = data[i], i + 1
+            while j < len(data) and j < i + 4 and (data[j] & 0xC0) == 0x80:
+                sym = (sym << 8) | data[j]
+                j += 1
+            out.append(sym)
+            i += 1
+            while i < len(data) and (data[i] & 0xC0) == 0x80:
+                i += 1
+        return out
+
+    def rename(sa, sb):
+        shorter = sa if len(sa) <= len(sb) else sb
+        ids = {}
+        for s in shorter:
+            ids.setdefault(s, len(ids) + 1)
+        return bytes(ids.get(s, 0) for s in sa), bytes(ids.get(s, 0) for s in sb)
+
+    pool = "aбвжzß日本語😀é x"
+    for _ in range(300):
+        a = "".join(rng.choice(pool) for _ in range(rng.randrange(0, 30)))
+        b = "".join(rng.choice(pool) for _ in range(rng.randrange(0, 30)))
+        sa, sb = symbols(a.encode()), symbols(b.encode())
+        assert len(sa) == len(a) and len(sb) == len(b)          # valid UTF-8: one symbol per code point
+        assert len(set(sa)) == len(set(a))                      # the packing is a bijection on the symbols present
+        ra, rb = rename(sa, sb)
+        assert pyref.levenshtein(ra, rb) == pyref.levenshtein(list(a), list(b)), (a, b)
