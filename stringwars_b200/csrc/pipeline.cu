@@ -342,26 +342,31 @@ swb_status_t swb::run_device_batch_utf8(swb_engine *eng, int dev_index, PairSpac
     // Element-wise pairs: ONE pass renames every pair to a byte alphabet (utf8_rename_kernel; pure-ASCII text goes through
     // it like any other) and the byte kernels do the rest.
     if (ps.n_c == 0 && eng->algorithm != SWB_ALGO_WAVEFRONT) {
-        SWB_CUDA(cudaMemsetAsync(d_flag + 1, 0, sizeof(uint32_t), stream));
         SWB_CUDA(ctx.ren_a.reserve(a_bytes + 64));
         SWB_CUDA(ctx.ren_b.reserve(b_bytes + 64));
         SWB_CUDA(ctx.ren_a_offs.reserve((2 * n_a + 2) * sizeof(uint64_t)));
         SWB_CUDA(ctx.ren_b_offs.reserve((2 * n_b + 2) * sizeof(uint64_t)));
         const unsigned blocks = (unsigned)((ps.n_pairs + RENAME_WARPS - 1) / RENAME_WARPS);
-        utf8_rename_kernel<<<blocks, 32 * RENAME_WARPS, 0, stream>>>(ps.a_data, ps.a_offs, a32, ps.b_data, ps.b_offs, b32, ps.n_pairs, (uint8_t *)ctx.ren_a.ptr,
-                                                                    (uint8_t *)ctx.ren_b.ptr, (uint64_t *)ctx.ren_a_offs.ptr, (uint64_t *)ctx.ren_b_offs.ptr,
-                                                                    d_flag + 1);
-        g_launches++;
-        SWB_CUDA(cudaGetLastError());
-        uint32_t h_overflow = 0;
-        SWB_CUDA(cudaMemcpyAsync(&h_overflow, d_flag + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-        SWB_CUDA(cudaStreamSynchronize(stream));
-        if (h_overflow == 0) {
-            PairSpace ren = ps;
-            ren.a_data = (const uint8_t *)ctx.ren_a.ptr, ren.a_offs = (const uint64_t *)ctx.ren_a_offs.ptr;
-            ren.b_data = (const uint8_t *)ctx.ren_b.ptr, ren.b_offs = (const uint64_t *)ctx.ren_b_offs.ptr;
-            ren.len_shift = 0, ren.offs32 = 0, ren.idx_shift = 1; // two strings per input string: the renamed one and the gap behind it
-            return run_device_batch(eng, dev_index, ren, stream, err);
+        // tier 0: ASCII keeps its bytes, 127 dictionary slots for the rest; tier 1: 255 slots for everything
+        for (int tier = 0; tier < 2; ++tier) {
+            SWB_CUDA(cudaMemsetAsync(d_flag + 1, 0, sizeof(uint32_t), stream));
+            auto kernel = tier == 0 ? utf8_rename_kernel<true> : utf8_rename_kernel<false>;
+            kernel<<<blocks, 32 * RENAME_WARPS, 0, stream>>>(ps.a_data, ps.a_offs, a32, a_bytes, ps.b_data, ps.b_offs, b32, b_bytes, ps.n_pairs,
+                                                             (uint8_t *)ctx.ren_a.ptr, (uint8_t *)ctx.ren_b.ptr, (uint64_t *)ctx.ren_a_offs.ptr,
+                                                             (uint64_t *)ctx.ren_b_offs.ptr, d_flag + 1);
+            g_launches++;
+            SWB_CUDA(cudaGetLastError());
+            uint32_t h_flags = 0;
+            SWB_CUDA(cudaMemcpyAsync(&h_flags, d_flag + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            SWB_CUDA(cudaStreamSynchronize(stream));
+            if (h_flags & RENAME_BAD_OFFSETS) return fail(err, SWB_INVALID_ARG, "offsets are not monotonic (or leave the tape, or a string spans 4 GiB or more)");
+            if (h_flags == 0) {
+                PairSpace ren = ps;
+                ren.a_data = (const uint8_t *)ctx.ren_a.ptr, ren.a_offs = (const uint64_t *)ctx.ren_a_offs.ptr;
+                ren.b_data = (const uint8_t *)ctx.ren_b.ptr, ren.b_offs = (const uint64_t *)ctx.ren_b_offs.ptr;
+                ren.len_shift = 0, ren.offs32 = 0, ren.idx_shift = 1; // two strings per input string: the renamed one and the gap behind it
+                return run_device_batch(eng, dev_index, ren, stream, err);
+            }
         }
     }
     // Cross products, pairs with too many distinct symbols, the explicit wavefront algorithm: 32-bit symbols
@@ -393,7 +398,23 @@ static swb_status_t device_span(const void *offs, uint32_t width, uint64_t n, cu
     SWB_CUDA(cudaMemcpyAsync(&ends[0], offs, width, cudaMemcpyDeviceToHost, stream));
     SWB_CUDA(cudaMemcpyAsync(&ends[1], (const uint8_t *)offs + n * width, width, cudaMemcpyDeviceToHost, stream));
     SWB_CUDA(cudaStreamSynchronize(stream));
-    *bytes = ends[1] - ends[0]; // little-endian: a u32 lands in the low half of the zeroed u64
+    if (ends[1] < ends[0]) return fail(err, SWB_INVALID_ARG, "offsets are not monotonic (last %llu < first %llu)", (unsigned long long)ends[1], (unsigned long long)ends[0]);
+    *bytes = ends[1] - ends[0];
+    return SWB_OK;
+}
+// Total bytes spanned by the strings of two DEVICE-readable offsets arrays (one small synchronous readback for both).
+static swb_status_t device_spans(const void *a_offs, uint32_t a_width, uint64_t n_a, uint64_t *a_bytes, const void *b_offs, uint32_t b_width, uint64_t n_b,
+                                 uint64_t *b_bytes, cudaStream_t stream, const char **err) {
+    uint64_t ends[4] = {0, 0, 0, 0}; // little-endian: a u32 lands in the low half of the zeroed u64
+    SWB_CUDA(cudaMemcpyAsync(&ends[0], a_offs, a_width, cudaMemcpyDeviceToHost, stream));
+    SWB_CUDA(cudaMemcpyAsync(&ends[1], (const uint8_t *)a_offs + n_a * a_width, a_width, cudaMemcpyDeviceToHost, stream));
+    SWB_CUDA(cudaMemcpyAsync(&ends[2], b_offs, b_width, cudaMemcpyDeviceToHost, stream));
+    SWB_CUDA(cudaMemcpyAsync(&ends[3], (const uint8_t *)b_offs + n_b * b_width, b_width, cudaMemcpyDeviceToHost, stream));
+    SWB_CUDA(cudaStreamSynchronize(stream));
+    if (ends[1] < ends[0] || ends[3] < ends[2])
+        return fail(err, SWB_INVALID_ARG, "offsets are not monotonic (last %llu < first %llu)", (unsigned long long)(ends[1] < ends[0] ? ends[1] : ends[3]),
+                    (unsigned long long)(ends[1] < ends[0] ? ends[0] : ends[2]));
+    *a_bytes = ends[1] - ends[0], *b_bytes = ends[3] - ends[2];
     return SWB_OK;
 }
 
@@ -418,8 +439,7 @@ extern "C" swb_status_t swb_compute_pairs_device(swb_engine_t *engine, int devic
     PairSpace ps = make_pair_space(a_data, a_offsets, b_data, b_offsets, n_pairs, 0, 0, out, 0, 0);
     if (engine->kind == ENGINE_LEVENSHTEIN_UTF8) {
         uint64_t a_bytes = 0, b_bytes = 0;
-        if ((st = device_span(a_offsets, 8, n_pairs, (cudaStream_t)cuda_stream, &a_bytes, err)) != SWB_OK) return st;
-        if ((st = device_span(b_offsets, 8, n_pairs, (cudaStream_t)cuda_stream, &b_bytes, err)) != SWB_OK) return st;
+        if ((st = device_spans(a_offsets, 8, n_pairs, &a_bytes, b_offsets, 8, n_pairs, &b_bytes, (cudaStream_t)cuda_stream, err)) != SWB_OK) return st;
         return run_device_batch_utf8(engine, device_index, ps, n_pairs, n_pairs, a_bytes, b_bytes, (cudaStream_t)cuda_stream, err);
     }
     return run_device_batch(engine, device_index, ps, (cudaStream_t)cuda_stream, err);
@@ -440,8 +460,7 @@ extern "C" swb_status_t swb_compute_pairs_device_view(swb_engine_t *engine, int 
     PairSpace ps = make_pair_space(a->data, a->offsets, b->data, b->offsets, a->n, 0, 0, out, (uint32_t)out_type, offs32);
     if (engine->kind == ENGINE_LEVENSHTEIN_UTF8) {
         uint64_t a_bytes = 0, b_bytes = 0;
-        if ((st = device_span(a->offsets, a->offset_bits / 8, a->n, (cudaStream_t)cuda_stream, &a_bytes, err)) != SWB_OK) return st;
-        if ((st = device_span(b->offsets, b->offset_bits / 8, b->n, (cudaStream_t)cuda_stream, &b_bytes, err)) != SWB_OK) return st;
+        if ((st = device_spans(a->offsets, a->offset_bits / 8, a->n, &a_bytes, b->offsets, b->offset_bits / 8, b->n, &b_bytes, (cudaStream_t)cuda_stream, err)) != SWB_OK) return st;
         return run_device_batch_utf8(engine, device_index, ps, a->n, b->n, a_bytes, b_bytes, (cudaStream_t)cuda_stream, err);
     }
     return run_device_batch(engine, device_index, ps, (cudaStream_t)cuda_stream, err);
@@ -460,8 +479,7 @@ extern "C" swb_status_t swb_compute_cross_device(swb_engine_t *engine, int devic
     PairSpace ps = make_pair_space(q_data, q_offsets, c_data, c_offsets, (uint64_t)n_queries * n_candidates, n_candidates, row_stride, out, 0, 0);
     if (engine->kind == ENGINE_LEVENSHTEIN_UTF8) {
         uint64_t a_bytes = 0, b_bytes = 0;
-        if ((st = device_span(q_offsets, 8, n_queries, (cudaStream_t)cuda_stream, &a_bytes, err)) != SWB_OK) return st;
-        if ((st = device_span(c_offsets, 8, n_candidates, (cudaStream_t)cuda_stream, &b_bytes, err)) != SWB_OK) return st;
+        if ((st = device_spans(q_offsets, 8, n_queries, &a_bytes, c_offsets, 8, n_candidates, &b_bytes, (cudaStream_t)cuda_stream, err)) != SWB_OK) return st;
         return run_device_batch_utf8(engine, device_index, ps, n_queries, n_candidates, a_bytes, b_bytes, (cudaStream_t)cuda_stream, err);
     }
     return run_device_batch(engine, device_index, ps, (cudaStream_t)cuda_stream, err);
@@ -770,8 +788,7 @@ static swb_status_t host_pairs(swb_engine *engine, const Side &A, const Side &B,
             // decode needs the whole shard resident: no chunk pipelining on this path
             SWB_CUDA(cudaStreamWaitEvent(ctx.compute_stream, ctx.ev_chunks[chunks - 1], 0));
             if (!host_offs) {
-                if ((st = device_span(sh.a.offs_at_lo, A.width, n, ctx.compute_stream, &sh.a_bytes, err)) != SWB_OK) return st;
-                if ((st = device_span(sh.b.offs_at_lo, B.width, n, ctx.compute_stream, &sh.b_bytes, err)) != SWB_OK) return st;
+                if ((st = device_spans(sh.a.offs_at_lo, A.width, n, &sh.a_bytes, sh.b.offs_at_lo, B.width, n, &sh.b_bytes, ctx.compute_stream, err)) != SWB_OK) return st;
             }
             if ((st = run_device_batch_utf8(engine, d, sh.ps, n, n, sh.a_bytes, sh.b_bytes, ctx.compute_stream, err)) != SWB_OK) return drain(scope), st;
             if (staged_out) SWB_CUDA(cudaMemcpyAsync(h_out, ctx.out.ptr, n * elt, cudaMemcpyDeviceToHost, ctx.compute_stream));

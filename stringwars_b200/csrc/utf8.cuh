@@ -84,119 +84,192 @@ __global__ void __launch_bounds__(256) utf8_pack_kernel(const uint8_t *data, con
 
 // Per-pair alphabet compaction for element-wise pairs. The bit-vector kernels index their match tables by BYTE, and an
 // edit distance only ever asks whether pattern symbol i equals text symbol j. So each pair's code points are renamed to
-// bytes: the distinct symbols of the pair's shorter string get the number of the slot they occupy in a 255-slot
-// open-addressing dictionary (shared memory, one per warp), the other string is translated through the same dictionary
-// and everything it holds that the shorter string does not becomes 0 (which equals no id). The renamed pair has exactly
-// the distance of the original and runs on the byte kernels.
-// ONE pass over the byte tapes does everything — symbol split, dictionary, translation: a round covers 512 bytes of a
-// string (a re-aligned 16-byte piece per lane); lanes mark their lead bytes, a warp prefix sum numbers the symbols, the
-// packed symbols go to a shared-memory staging row, and the dictionary work then runs one symbol per lane, all 32 lanes
-// busy, with coalesced byte stores. There is no symbol count / scan pass: renamed string i is written at the byte offset
-// of the original string i, and the output tape has TWO strings per input string — the renamed string and the gap behind
-// it — so a PairSpace with idx_shift = 1 addresses it (out_offs[2 i] = start, out_offs[2 i + 1] = end).
-// A pair whose dictionary fills up (more than ~250 distinct code points in its shorter string) raises `overflow`; the
-// host then keeps the batch on the 32-bit wavefront kernel.
+// bytes and the renamed pair, which has exactly the distance of the original, runs on the byte kernels.
+//   ASCII_IDENTITY: a one-byte symbol below 0x80 keeps its value — no dictionary work at all for it. Every other symbol of
+//     the pair's shorter string (in bytes) is numbered 129, 130, ... in the order a per-warp open-addressing dictionary
+//     (shared memory) first meets it; the other string is translated through the same dictionary and what it holds that
+//     the shorter string does not becomes 128, which equals no id. Room for 127 distinct multi-byte symbols.
+//   otherwise (second tier): every symbol goes through the dictionary, ids 1..255, 0 for "not in the shorter string".
+// ONE pass over the byte tapes does everything — symbol split, dictionary, translation. A round covers 512 bytes of a
+// string, a re-aligned 16-byte piece per lane. A lane marks its lead bytes (a symbol starts at every byte that is not
+// 10xxxxxx and takes up to three continuation bytes: the oracle's rule); one warp prefix sum gives it its place in the
+// staging row of ids and in the list of the round's dictionary symbols; plain ASCII goes straight to the row, the rest to
+// the list, and the list is then worked off ONE SYMBOL PER LANE, all 32 lanes busy whatever the mix of scripts: probe,
+// insert (atomicCAS), number the newcomers of the step with a ballot, write the id into the row. The row leaves as aligned
+// 32-bit stores. There is no symbol count / scan pass: renamed string i is written at the byte offset of the original
+// string i, and the output tape has TWO strings per input string — the renamed string and the gap behind it — so a
+// PairSpace with idx_shift = 1 addresses it (out_offs[2 i] = start, out_offs[2 i + 1] = end).
+// `flags`: bit 0 is raised by a pair with more distinct symbols than ids (the host goes to the next tier: the 255-id
+// variant, then the 32-bit wavefront kernel), bit 1 by a string whose offsets run backwards or leave the tape's span (the
+// call fails with SWB_INVALID_ARG; the pair is renamed to two empty strings and nothing outside the span is read).
 constexpr int RENAME_WARPS = 4;
-constexpr uint32_t RENAME_SLOTS = 256;        // slot 0 is never used: ids are 1..255
-constexpr uint32_t RENAME_EMPTY = 0xFFFFFFFFu; // no packed UTF-8 symbol: continuation bytes are never 0xFF
+constexpr uint32_t RENAME_TABLE = 512;         // dictionary slots: at most 255 are ever numbered, so probes are short
+constexpr uint32_t RENAME_EMPTY = 0xFFFFFFFFu; // no packed symbol: byte 0 is a lead, bytes 1..3 continuation bytes (never 0xFF) or absent (0)
+constexpr uint32_t RENAME_OVERFLOW = 1u, RENAME_BAD_OFFSETS = 2u;
 
-__device__ __forceinline__ uint32_t rename_slot(uint32_t key) { return 1u + ((key * 0x9E3779B1u) >> 8) % 255u; }
+// bit k: byte k of the word is >= 0x80
+__device__ __forceinline__ uint32_t high_bits4(uint32_t w) { return ((((w >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu; }
 
+struct RenameShared {
+    uint32_t keys[RENAME_TABLE];       // the dictionary: packed symbols
+    uint32_t list[512];                // the round's dictionary symbols: byte position in the round | place in the row << 16
+    uint32_t ext[32];                  // the lanes' symbol-end bits (see below)
+    uint8_t key_id[RENAME_TABLE];      // id of the symbol in slot h
+    alignas(16) uint8_t raw[512 + 16]; // the round's bytes
+    alignas(16) uint8_t row[512 + 16]; // ids of the round's symbols, in order
+};
+
+template <bool ASCII_IDENTITY>
 __global__ void __launch_bounds__(32 * RENAME_WARPS)
-    utf8_rename_kernel(const uint8_t *a_data, const void *a_offs, uint32_t a32, const uint8_t *b_data, const void *b_offs, uint32_t b32, uint64_t n_pairs,
-                       uint8_t *a_out, uint8_t *b_out, uint64_t *a_oo, uint64_t *b_oo, uint32_t *overflow) {
-    __shared__ uint32_t s_keys[RENAME_WARPS][RENAME_SLOTS];
-    __shared__ uint32_t s_syms[RENAME_WARPS][512];
+    utf8_rename_kernel(const uint8_t *a_data, const void *a_offs, uint32_t a32, uint64_t a_span, const uint8_t *b_data, const void *b_offs, uint32_t b32,
+                       uint64_t b_span, uint64_t n_pairs, uint8_t *a_out, uint8_t *b_out, uint64_t *a_oo, uint64_t *b_oo, uint32_t *flags) {
+    constexpr uint32_t CAP = ASCII_IDENTITY ? 127u : 255u, ID_BASE = ASCII_IDENTITY ? 128u : 0u; // ids ID_BASE + 1 .. ID_BASE + CAP; ID_BASE = "absent"
+    __shared__ __align__(16) RenameShared shared[RENAME_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t pair = (uint64_t)blockIdx.x * RENAME_WARPS + warp;
     if (pair >= n_pairs) return;
-    uint32_t *keys = s_keys[warp], *syms = s_syms[warp];
+    RenameShared &sh = shared[warp];
     const uint64_t a_base = tape_offset(a_offs, a32, 0), b_base = tape_offset(b_offs, b32, 0);
-    const uint64_t ab0 = tape_offset(a_offs, a32, pair), ab1 = tape_offset(a_offs, a32, pair + 1), bb0 = tape_offset(b_offs, b32, pair),
-                   bb1 = tape_offset(b_offs, b32, pair + 1);
-    const uint32_t a_len = ab1 < ab0 ? 0u : (uint32_t)(ab1 - ab0), b_len = bb1 < bb0 ? 0u : (uint32_t)(bb1 - bb0); // bytes
-    for (uint32_t i = lane; i < RENAME_SLOTS; i += 32) keys[i] = RENAME_EMPTY;
+    uint64_t ab0 = tape_offset(a_offs, a32, pair), ab1 = tape_offset(a_offs, a32, pair + 1), bb0 = tape_offset(b_offs, b32, pair),
+             bb1 = tape_offset(b_offs, b32, pair + 1);
+    if (ab0 < a_base || ab1 < ab0 || ab1 - a_base > a_span || ((ab1 - ab0) >> 32) != 0u || bb0 < b_base || bb1 < bb0 || bb1 - b_base > b_span ||
+        ((bb1 - bb0) >> 32) != 0u) {
+        if (lane == 0) atomicOr(flags, RENAME_BAD_OFFSETS);
+        ab0 = ab1 = a_base, bb0 = bb1 = b_base;
+    }
+    const uint32_t a_len = (uint32_t)(ab1 - ab0), b_len = (uint32_t)(bb1 - bb0); // bytes
+#pragma unroll
+    for (uint32_t i = 0; i < RENAME_TABLE / 128; ++i)
+        reinterpret_cast<uint4 *>(sh.keys)[i * 32 + lane] = make_uint4(RENAME_EMPTY, RENAME_EMPTY, RENAME_EMPTY, RENAME_EMPTY);
     __syncwarp();
     bool failed = false;
+    uint32_t n_ids = 0; // symbols numbered so far (the same in every lane)
+    const bool a_first = a_len <= b_len;
+    uint32_t n_symbols[2];
 
-    // Renames one string; DICT: its symbols enter the dictionary. Returns the number of symbols (same in every lane).
-    auto rename = [&](const uint8_t *str, uint32_t len, uint8_t *out, auto dict_tag) -> uint32_t {
-        constexpr bool DICT = decltype(dict_tag)::value;
+    // Pass 0 renames the shorter string, whose symbols enter the dictionary; pass 1 translates the other one. One body for
+    // both (the loop is not unrolled): the code stays small enough for the instruction cache.
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool dict = pass == 0, is_a = a_first == dict;
+        const uint8_t *str = is_a ? a_data + ab0 : b_data + bb0;
+        const uint32_t len = is_a ? a_len : b_len;
+        uint8_t *out = is_a ? a_out + (ab0 - a_base) : b_out + (bb0 - b_base);
         PieceStream st;
         st.open(str, len, 0u);
         uint32_t nsym = 0;
+#pragma unroll 1
         for (uint32_t base = 0; 16u * base < len; base += 32) {
             const uint32_t i = base + (uint32_t)lane;
             const bool live = 16u * i < len;
             uint4 p = make_uint4(0, 0, 0, 0);
-            uint32_t ahead = 0; // the four bytes after the piece (continuation bytes of a symbol that starts near its end)
-            if (live) {
-                p = st.piece(i);
-                if (16u * (i + 1u) < len) ahead = st.piece(i + 1u).x;
-            }
+            if (live) p = st.piece(i);
+            // the four bytes after the piece (continuation bytes of a symbol that starts near its end): the next lane's
+            uint32_t ahead = __shfl_down_sync(0xffffffffu, p.x, 1);
+            if (lane == 31) ahead = 16u * (i + 1u) < len ? st.piece(i + 1u).x : 0u;
             const uint32_t remaining = live ? len - 16u * i : 0u; // bytes of the string from this piece's first byte on
             const uint32_t valid = remaining >= 16u ? 0xFFFFu : ((1u << remaining) - 1u);
-            uint32_t leads = live ? (lead_bits16(p) & valid) : 0u;
-            const uint32_t mine = __popc(leads);
-            uint32_t upto = mine; // inclusive scan over lanes
+            // bit j of ext: byte j of the 20 ends the symbol before it (a lead byte, or the end of the string)
+            const uint32_t ext = lead_bits16(p) | (lead_bits4(ahead) << 16) | (remaining >= 20u ? 0u : 0xFFFFFFFFu << remaining);
+            const uint32_t leads = ext & valid;
+            const uint32_t high = high_bits4(p.x) | (high_bits4(p.y) << 4) | (high_bits4(p.z) << 8) | (high_bits4(p.w) << 12);
+            const uint32_t plain = ASCII_IDENTITY ? (leads & ~high & (ext >> 1)) : 0u; // one-byte symbols below 0x80
+            const uint32_t listed = leads & ~plain;
+            const uint32_t mine = __popc(leads) | (__popc(listed) << 16);
+            uint32_t upto = mine; // inclusive scan over lanes of both counts at once
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t up = __shfl_up_sync(0xffffffffu, upto, d);
                 if (lane >= d) upto += up;
             }
-            const uint32_t total = __shfl_sync(0xffffffffu, upto, 31);
-            uint32_t k = upto - mine;
-            const uint32_t words[5] = {p.x, p.y, p.z, p.w, ahead};
-            while (leads) { // stage this piece's packed symbols (lead byte + up to three continuation bytes, big-endian)
-                const uint32_t j = __ffs(leads) - 1u;
-                leads &= leads - 1u;
-                const uint32_t four = __funnelshift_r(words[j >> 2], words[(j >> 2) + 1u], 8u * (j & 3u)); // bytes j .. j + 3
-                uint32_t sym = four & 0xFFu;
-                const uint32_t room = remaining - j; // bytes of the string from byte j on (>= 1)
-                if (room > 1u && ((four >> 8) & 0xC0u) == 0x80u) {
-                    sym = (sym << 8) | ((four >> 8) & 0xFFu);
-                    if (room > 2u && ((four >> 16) & 0xC0u) == 0x80u) {
-                        sym = (sym << 8) | ((four >> 16) & 0xFFu);
-                        if (room > 3u && ((four >> 24) & 0xC0u) == 0x80u) sym = (sym << 8) | (four >> 24);
-                    }
+            const uint32_t totals = __shfl_sync(0xffffffffu, upto, 31);
+            const uint32_t total = totals & 0xFFFFu, n_listed = totals >> 16;
+            const uint32_t k = (upto - mine) & 0xFFFFu, s = (upto - mine) >> 16;
+            // the bytes and the symbol ends, for the lanes that work the list off
+            *reinterpret_cast<uint4 *>(sh.raw + 16 * lane) = p;
+            if (lane == 31) *reinterpret_cast<uint32_t *>(sh.raw + 512) = ahead;
+            sh.ext[lane] = ext;
+            if (ASCII_IDENTITY && plain == 0xFFFFu && (k & 3u) == 0u) {
+                // sixteen one-byte symbols: the ids are the bytes
+                uint32_t *d32 = reinterpret_cast<uint32_t *>(sh.row + k);
+                d32[0] = p.x, d32[1] = p.y, d32[2] = p.z, d32[3] = p.w;
+            } else if (leads) {
+                // straight-line, predicated: plain ASCII to its place in the row, everything else to the list
+                const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+                const uint32_t here = 16u * (uint32_t)lane + (k << 16);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t before = (1u << j) - 1u;
+                    const uint32_t kj = k + __popc(leads & before);
+                    if (ASCII_IDENTITY && ((plain >> j) & 1u)) sh.row[kj] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+                    if ((listed >> j) & 1u) sh.list[s + __popc(listed & before)] = here + (uint32_t)j + (__popc(leads & before) << 16);
                 }
-                syms[k++] = sym;
             }
             __syncwarp();
-            for (uint32_t q = lane; q < total; q += 32) { // one symbol per lane: dictionary lookup / insertion
-                const uint32_t key = syms[q];
-                uint32_t h = rename_slot(key), id = 0;
-                for (uint32_t probes = 0; probes < 255u; ++probes, h = h == 255u ? 1u : h + 1u) {
-                    uint32_t at = keys[h];
-                    if (DICT && at == RENAME_EMPTY) at = atomicCAS(&keys[h], RENAME_EMPTY, key) == RENAME_EMPTY ? key : keys[h];
-                    if (at == key) {
-                        id = h;
-                        break;
+            // the round's dictionary symbols, one per lane
+            for (uint32_t q0 = 0; q0 < n_listed; q0 += 32) {
+                const uint32_t q = q0 + (uint32_t)lane;
+                const bool active = q < n_listed;
+                const uint32_t entry = active ? sh.list[q] : 0u;
+                const uint32_t pos = entry & 0xFFFFu, at_row = entry >> 16;
+                const uint32_t *word = reinterpret_cast<const uint32_t *>(sh.raw + (pos & ~3u));
+                const uint32_t four = __funnelshift_r(word[0], word[1], 8u * (pos & 3u));                    // bytes pos .. pos + 3
+                const uint32_t conts = __ffs(((sh.ext[pos >> 4] >> ((pos & 15u) + 1u)) & 7u) | 8u) - 1u; // continuation bytes taken: 0..3
+                const uint32_t key = four & (0xFFFFFFFFu >> (24u - 8u * conts));
+                uint32_t h = (key * 0x9E3779B1u) >> 23;
+                bool won = false, found = false;
+                if (active) {
+#pragma unroll 1
+                    for (uint32_t probes = 0; probes < RENAME_TABLE; ++probes, h = (h + 1u) & (RENAME_TABLE - 1u)) {
+                        uint32_t at = sh.keys[h];
+                        if (dict && at == RENAME_EMPTY) {
+                            at = atomicCAS(&sh.keys[h], RENAME_EMPTY, key);
+                            if (at == RENAME_EMPTY) {
+                                won = true;
+                                break;
+                            }
+                        }
+                        if (at == key) {
+                            found = true;
+                            break;
+                        }
+                        if (at == RENAME_EMPTY) break; // not in the dictionary
                     }
-                    if (at == RENAME_EMPTY) break; // not in the dictionary: stays 0
                 }
-                if (DICT && id == 0u) failed = true; // dictionary full
-                out[nsym + q] = (uint8_t)id;
+                if (dict) { // the step's newcomers take the next numbers, in lane order
+                    const uint32_t winners = __ballot_sync(0xffffffffu, won);
+                    if (won) {
+                        const uint32_t number = n_ids + __popc(winners & ((1u << lane) - 1u)) + 1u;
+                        if (number > CAP) failed = true;
+                        sh.key_id[h] = (uint8_t)(ID_BASE + number);
+                    }
+                    n_ids += __popc(winners);
+                    if (active && !won && !found) failed = true; // table full (only after the ids ran out)
+                    __syncwarp();
+                    found = found || won;
+                }
+                if (active) sh.row[at_row] = found ? sh.key_id[h] : (uint8_t)ID_BASE;
             }
+            __syncwarp();
+            // the row leaves as aligned 32-bit words; the bytes before the first and after the last whole word one by one
+            uint8_t *dst = out + nsym;
+            const uint32_t head = min(total, (uint32_t)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u));
+            const uint32_t words = (total - head) >> 2, tail = head + 4u * words;
+            if ((uint32_t)lane < head) dst[lane] = sh.row[lane];
+            const uint32_t *row32 = reinterpret_cast<const uint32_t *>(sh.row);
+            uint32_t *dst32 = reinterpret_cast<uint32_t *>(dst + head);
+            for (uint32_t w = lane; w < words; w += 32) dst32[w] = __funnelshift_r(row32[w], row32[w + 1], 8u * head);
+            if (tail + (uint32_t)lane < total) dst[tail + lane] = sh.row[tail + lane];
             __syncwarp();
             nsym += total;
         }
-        return nsym;
-    };
-    const bool dict_is_a = a_len <= b_len;
-    uint32_t na, nb;
-    if (dict_is_a) {
-        na = rename(a_data + ab0, a_len, a_out + (ab0 - a_base), std::true_type{});
-        nb = rename(b_data + bb0, b_len, b_out + (bb0 - b_base), std::false_type{});
-    } else {
-        nb = rename(b_data + bb0, b_len, b_out + (bb0 - b_base), std::true_type{});
-        na = rename(a_data + ab0, a_len, a_out + (ab0 - a_base), std::false_type{});
+        n_symbols[is_a ? 0 : 1] = nsym;
     }
     if (lane == 0) {
-        a_oo[2 * pair] = ab0 - a_base, a_oo[2 * pair + 1] = ab0 - a_base + na;
-        b_oo[2 * pair] = bb0 - b_base, b_oo[2 * pair + 1] = bb0 - b_base + nb;
+        a_oo[2 * pair] = ab0 - a_base, a_oo[2 * pair + 1] = ab0 - a_base + n_symbols[0];
+        b_oo[2 * pair] = bb0 - b_base, b_oo[2 * pair + 1] = bb0 - b_base + n_symbols[1];
     }
-    if (__any_sync(0xffffffffu, failed) && lane == 0) atomicOr(overflow, 1u);
+    if (__any_sync(0xffffffffu, failed) && lane == 0) atomicOr(flags, RENAME_OVERFLOW);
 }
 
 } // namespace swb

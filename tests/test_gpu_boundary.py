@@ -336,8 +336,18 @@ def test_non_monotonic_offsets_are_refused_not_faulted(scope, lev):
         lev.compute_pairs_device(ad.data_ptr(), ao.data_ptr(), bd.data_ptr(), bo.data_ptr(), len(a), out.data_ptr())
     assert e.value.status_name == "INVALID_ARG"
     torch.cuda.synchronize()
-    # and the engine still works afterwards
+    # the code-point engine reads the tapes in its rename pass, before any statistics: it validates for itself
+    utf8 = sw.LevenshteinDistancesUtf8(scope)
+    with pytest.raises(sw.Error) as e:
+        utf8.compute_pairs_device(ad.data_ptr(), ao.data_ptr(), bd.data_ptr(), bo.data_ptr(), len(a), out.data_ptr())
+    assert e.value.status_name == "INVALID_ARG"
+    with pytest.raises(sw.Error) as e:
+        utf8.compute_pairs(scope, broken, b)
+    assert e.value.status_name == "INVALID_ARG"
+    torch.cuda.synchronize()
+    # and the engines still work afterwards
     assert lev.compute_pairs(scope, a.subview(0, 100), b.subview(0, 100)).shape == (100,)
+    assert np.array_equal(utf8.compute_pairs(scope, a.subview(0, 100), b.subview(0, 100)), lev.compute_pairs(scope, a.subview(0, 100), b.subview(0, 100)))
 
 
 def test_scope_destroyed_before_its_engines_and_tapes():
@@ -435,6 +445,15 @@ def test_codepoint_engine_alphabet_compaction_and_its_fallback(scope, oracle):
     ta, tb = BytesTape.from_strings(sa), BytesTape.from_strings(sb)
     want = oracle.levenshtein_pairs(ta.data, ta.offsets, tb.data, tb.offsets, oracle.UTF8, threads=8)
     assert np.array_equal(utf8.compute_pairs(scope, ta, tb), want), utf8.last_kernel
+    # 128..255 distinct multi-byte code points in the shorter string of ONE pair: the second rename tier (a 255-slot
+    # dictionary for every symbol) keeps the batch on the byte kernels; arbitrary bytes (not UTF-8 at all) split like the oracle
+    mid = "".join(chr(0x4E00 + i) for i in range(200))
+    junk = [bytes(rng.choice([0x41, 0x00, 0x7F, 0x80, 0xBF, 0xC3, 0xE4, 0xF0, 0xFF, 0x20], size=int(rng.integers(0, 70))).astype(np.uint8)) for _ in range(400)]
+    ta = BytesTape.from_strings([x.encode() for x in sa[:50]] + [mid.encode()] + junk[:200])
+    tb = BytesTape.from_strings([x.encode() for x in sb[:50]] + [(mid[::-1] + "ж" + mid[:10]).encode()] + junk[200:])
+    want = oracle.levenshtein_pairs(ta.data, ta.offsets, tb.data, tb.offsets, oracle.UTF8, threads=8)
+    assert np.array_equal(utf8.compute_pairs(scope, ta, tb), want)
+    assert "wavefront" not in utf8.last_kernel, utf8.last_kernel
     # more than 255 distinct code points in the shorter string of ONE pair: whole batch falls back, still exact
     wide = "".join(chr(0x4E00 + i) for i in range(300))
     sa2, sb2 = sa[:50] + [wide], sb[:50] + [wide[::-1] + "ж"]

@@ -429,50 +429,104 @@ def test_short_kernel_match_mask_in_registers():
         assert short_distance(pat, txt, W) == pyref.levenshtein(pat, txt), (pat, txt, W)
 
 
+def _lead_bits4(w):
+    cont = (w >> 7) & ~(w >> 6) & 0x01010101
+    lead = cont ^ 0x01010101
+    return ((lead * 0x01020408) >> 24) & 0xF
+
+
+def _rename_model(dict_str: bytes, other: bytes, ascii_identity: bool):
+    """utf8.cuh utf8_rename_kernel, piece by piece as a lane sees it: 16 bytes + the 4 bytes after them, `ext` bits (a lead
+    byte or the end of the string ends the symbol before it), little-endian packing of a lead byte and up to three
+    continuation bytes, plain ASCII kept as it is, everything else numbered through a dictionary (the kernel numbers
+    the newcomers of a 32-symbol step in lane order; any order gives the same distance). Returns the two renamed strings, or None when the dictionary overflows."""
+    cap, id_base = (127, 128) if ascii_identity else (255, 0)
+    numbers = {}  # the dictionary: packed symbol -> number, in the order the symbols are first met
+
+    def lookup(key, insert):
+        if key not in numbers:
+            if not insert:
+                return id_base
+            if len(numbers) == cap:
+                raise OverflowError
+            numbers[key] = len(numbers) + 1
+        return id_base + numbers[key]
+
+    def rename(data, insert):
+        out = bytearray()
+        for at in range(0, len(data), 16):
+            remaining = len(data) - at
+            window = data[at: at + 20] + bytes(rng_garbage.randrange(256) for _ in range(20))  # past the end: somebody else's bytes
+            words = [int.from_bytes(window[4 * q: 4 * q + 4], "little") for q in range(5)]
+            if remaining <= 16:
+                words[4] = 0  # no next piece: the kernel does not load one
+            ext = sum(_lead_bits4(words[q]) << (4 * q) for q in range(5))
+            if remaining < 20:
+                ext |= (M32 << remaining) & M32
+            valid = 0xFFFF if remaining >= 16 else (1 << remaining) - 1
+            leads = ext & valid
+            high = (words[0] | words[1] | words[2] | words[3]) & 0x80808080
+            if ascii_identity and high == 0 and (ext & 0x1FFFF) == 0x1FFFF:
+                out += window[:bin(leads).count("1")]  # the fast path stages 16 bytes; `total` keeps the symbols only
+                continue
+            for j in range(16):
+                if not (leads >> j) & 1:
+                    continue
+                four = int.from_bytes(window[j: j + 4], "little")
+                z = ((ext >> (j + 1)) & 7) | 8
+                conts = (z & -z).bit_length() - 1
+                if ascii_identity and conts == 0 and not four & 0x80:
+                    out.append(four & 0x7F)
+                else:
+                    out.append(lookup(four & (M32 >> (24 - 8 * conts)), insert))
+        return bytes(out)
+
+    try:
+        return rename(dict_str, True), rename(other, False)
+    except OverflowError:
+        return None
+
+
+rng_garbage = random.Random(77)
+
+
+def _tape(strings):
+    data = np.frombuffer(b"".join(strings) + b"\0", dtype=np.uint8)[:-1].copy()
+    offs = np.zeros(len(strings) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(x) for x in strings])
+    return data, offs
+
+
 def test_utf8_symbol_split_and_rename_model():
-    """utf8.cuh: lead bits of a word (a byte starts a symbol iff it is not 10xxxxxx), symbols packed big-endian from a lead
-    byte and up to three continuation bytes, and the per-pair rename (dictionary of the shorter string, everything else 0)
-    preserve the code-point distance."""
-    def lead_bits4(w):
-        cont = (w >> 7) & ~(w >> 6) & 0x01010101
-        lead = cont ^ 0x01010101
-        return ((lead * 0x01020408) >> 24) & 0xF
+    """utf8.cuh: lead bits of a word (a byte starts a symbol iff it is not 10xxxxxx), and the per-pair rename — ASCII kept,
+    other symbols numbered by dictionary slot, symbols the shorter string does not hold collapsed to one id — preserves the
+    code-point distance, on valid text and on arbitrary bytes (the oracle's lenient split)."""
+    from oracle import oracle
 
     rng = random.Random(9)
     for _ in range(2000):
         bs = bytes(rng.choice([0x41, 0x7F, 0x80, 0xBF, 0xC3, 0xE4, 0xF0, 0x00, 0xFF]) for _ in range(4))
-        w = int.from_bytes(bs, "little")
-        assert lead_bits4(w) == sum(1 << i for i in range(4) if (bs[i] & 0xC0) != 0x80), bs
-
-    def symbols(data):
-        out, i = [], 0
-        while i < len(data):
-            if (data[i] & 0xC0) == 0x80:  # stray continuation byte before any lead: ignored
-                i += 1
-                continue
-            sym, j = data[i], i + 1
-            while j < len(data) and j < i + 4 and (data[j] & 0xC0) == 0x80:
-                sym = (sym << 8) | data[j]
-                j += 1
-            out.append(sym)
-            i += 1
-            while i < len(data) and (data[i] & 0xC0) == 0x80:
-                i += 1
-        return out
-
-    def rename(sa, sb):
-        shorter = sa if len(sa) <= len(sb) else sb
-        ids = {}
-        for s in shorter:
-            ids.setdefault(s, len(ids) + 1)
-        return bytes(ids.get(s, 0) for s in sa), bytes(ids.get(s, 0) for s in sb)
+        assert _lead_bits4(int.from_bytes(bs, "little")) == sum(1 << i for i in range(4) if (bs[i] & 0xC0) != 0x80), bs
 
     pool = "aбвжzß日本語😀é x"
-    for _ in range(300):
-        a = "".join(rng.choice(pool) for _ in range(rng.randrange(0, 30)))
-        b = "".join(rng.choice(pool) for _ in range(rng.randrange(0, 30)))
-        sa, sb = symbols(a.encode()), symbols(b.encode())
-        assert len(sa) == len(a) and len(sb) == len(b)          # valid UTF-8: one symbol per code point
-        assert len(set(sa)) == len(set(a))                      # the packing is a bijection on the symbols present
-        ra, rb = rename(sa, sb)
-        assert pyref.levenshtein(ra, rb) == pyref.levenshtein(list(a), list(b)), (a, b)
+    nasty = [0x41, 0x00, 0x7F, 0x80, 0xBF, 0xC3, 0xE4, 0xF0, 0xFF, 0x20]
+    for trial in range(400):
+        if trial % 2:
+            a = "".join(rng.choice(pool) for _ in range(rng.randrange(0, 40))).encode()
+            b = "".join(rng.choice(pool) for _ in range(rng.randrange(0, 40))).encode()
+            want = pyref.levenshtein_utf8(a, b)
+        else:  # not UTF-8 at all: stray continuation bytes, overlong runs of them, lone leads, strings that end inside a symbol
+            a = bytes(rng.choice(nasty) for _ in range(rng.randrange(0, 50)))
+            b = bytes(rng.choice(nasty) for _ in range(rng.randrange(0, 50)))
+            want = int(oracle.levenshtein_pairs(*_tape([a]), *_tape([b]), oracle.UTF8)[0])
+        for ascii_identity in (True, False):
+            d, o = (a, b) if len(a) <= len(b) else (b, a)
+            ren = _rename_model(d, o, ascii_identity)
+            assert ren is not None
+            assert pyref.levenshtein(ren[0], ren[1]) == want, (a, b, ascii_identity)
+    # capacity: 127 distinct multi-byte symbols fit the first tier, 128 do not; the second tier takes 255 symbols of any kind
+    wide = "".join(chr(0x4E00 + i) for i in range(300))
+    assert _rename_model(wide[:127].encode(), wide.encode(), True) is not None
+    assert _rename_model(wide[:128].encode(), wide.encode(), True) is None
+    assert _rename_model((wide[:200] + "abc").encode(), wide.encode(), False) is not None
+    assert _rename_model(wide[:256].encode(), wide.encode(), False) is None
