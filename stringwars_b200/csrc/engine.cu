@@ -80,6 +80,10 @@ static void destroy_ctx(DeviceCtx &c) {
     if (c.side_stream) cudaStreamDestroy(c.side_stream);
     if (c.comm_stream) cudaStreamDestroy(c.comm_stream);
     if (c.ev_inputs) cudaEventDestroy(c.ev_inputs);
+    for (auto st : c.class_streams)
+        if (st) cudaStreamDestroy(st);
+    for (auto ev : c.ev_class)
+        if (ev) cudaEventDestroy(ev);
     if (c.ev_t0) cudaEventDestroy(c.ev_t0);
     if (c.ev_t1) cudaEventDestroy(c.ev_t1);
     if (c.d_stats) cudaFree(c.d_stats);
@@ -155,6 +159,10 @@ extern "C" swb_status_t swb_scope_create_devices(const int *devices, int num_dev
             if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c.comm_stream, cudaStreamNonBlocking, greatest);
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c.ev_inputs, cudaEventDisableTiming);
+        for (int k = 0; k < DeviceCtx::CLASS_STREAMS && e == cudaSuccess; ++k) {
+            e = cudaStreamCreateWithFlags(&c.class_streams[k], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c.ev_class[k], cudaEventDisableTiming);
+        }
         if (e == cudaSuccess) e = cudaEventCreate(&c.ev_t0);
         if (e == cudaSuccess) e = cudaEventCreate(&c.ev_t1);
         if (e == cudaSuccess) e = cudaMalloc(&c.d_stats, sizeof(ScheduleStats));

@@ -83,6 +83,11 @@ struct DeviceCtx {
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
     cudaStream_t side_stream = nullptr; // schedule kernel of speculative device-resident calls
     cudaEvent_t ev_inputs = nullptr;    // "caller's stream has reached this call": inputs are ready
+    // The length classes of a ragged batch run beside each other: class kernels have tails (a wave of the longest pairs)
+    // and small classes do not fill the machine; the largest class stays on the caller's stream.
+    static constexpr int CLASS_STREAMS = 3;
+    cudaStream_t class_streams[CLASS_STREAMS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_class[CLASS_STREAMS] = {nullptr, nullptr, nullptr};
     ScheduleStats *d_stats = nullptr;
     ScheduleStats *h_stats = nullptr;     // pinned + mapped: the schedule kernel publishes into it directly
     ScheduleStats *h_stats_dev = nullptr; // device alias of h_stats

@@ -290,6 +290,35 @@ swb_status_t swb::run_device_batch(swb_engine *eng, int dev_index, PairSpace ps,
     eng->spec_class = kernel_now, eng->spec_max_n = plan.n_classes ? plan.max_n[0] : 0u;
     if (have_stats && kernel_now == spec && eng->spec_max_n <= spec_cap) return SWB_OK; // the bet held: that kernel is the batch
     if (!plan.identity && (st = enqueue_scatter(ctx, ps, stream, err)) != SWB_OK) return st;
+    // Byte-Levenshtein classes run beside each other (they share nothing but read-only tapes; only the topmost class can
+    // need the strip scratch): the class with the most cells on the caller's stream, the others forked from it and joined
+    // back. Alignment classes share scratch rows and stay in line.
+    int on_side = 0;
+    if (plan.n_classes > 1 && lev_bytes && eng->algorithm != SWB_ALGO_WAVEFRONT) {
+        int biggest = 0;
+        auto cells = [&](int i) { return (double)plan.count[i] * plan.max_m[i] * plan.max_n[i]; };
+        for (int i = 1; i < plan.n_classes; ++i)
+            if (cells(i) > cells(biggest)) biggest = i;
+        SWB_CUDA(cudaEventRecord(ctx.ev_inputs, stream));
+        st = launch_class(eng, ctx, dev_index, ps, plan.begin[biggest], plan.count[biggest], plan.max_m[biggest], plan.max_n[biggest], stream, err, plan.same_shape);
+        if (st != SWB_OK) return st;
+        const char *main_kernel = eng->last_kernel;
+        for (int i = 0; i < plan.n_classes; ++i) {
+            if (i == biggest || plan.count[i] == 0) continue;
+            const int slot = on_side % DeviceCtx::CLASS_STREAMS;
+            cudaStream_t side = ctx.class_streams[slot];
+            if (on_side < DeviceCtx::CLASS_STREAMS) SWB_CUDA(cudaStreamWaitEvent(side, ctx.ev_inputs, 0));
+            st = launch_class(eng, ctx, dev_index, ps, plan.begin[i], plan.count[i], plan.max_m[i], plan.max_n[i], side, err, plan.same_shape);
+            if (st != SWB_OK) return st;
+            ++on_side;
+        }
+        for (int slot = 0; slot < std::min(on_side, (int)DeviceCtx::CLASS_STREAMS); ++slot) {
+            SWB_CUDA(cudaEventRecord(ctx.ev_class[slot], ctx.class_streams[slot]));
+            SWB_CUDA(cudaStreamWaitEvent(stream, ctx.ev_class[slot], 0));
+        }
+        eng->last_kernel = main_kernel;
+        return SWB_OK;
+    }
     for (int i = 0; i < plan.n_classes; ++i) {
         st = launch_class(eng, ctx, dev_index, ps, plan.begin[i], plan.count[i], plan.max_m[i], plan.max_n[i], stream, err, plan.same_shape);
         if (st != SWB_OK) return st;
