@@ -30,7 +30,10 @@ cases = {
     "coop G=32 K=2/4 + strips": (datasets._ragged(np.array([2048, 3000, 4096, 4500, 5]), alpha, rng, False), datasets._ragged(np.array([2048, 3100, 4096, 4600, 4800]), alpha, rng, False)),
     "mixed (bucketed)": datasets.utf8_line_pairs(300, 10, 400),
 }
-long_cases = {"coop strips + chunks": (datasets._ragged(np.array([9000, 4097, 30]), alpha, rng, False), datasets._ragged(np.array([9500, 5000, 40000]), alpha, rng, False))}
+ONLY_CHANGED = os.environ.get("SWB_PROBE_ONLY") == "utf8"  # racecheck of the rename pass and the forked class streams alone
+if ONLY_CHANGED:
+    cases = {"mixed (bucketed)": cases["mixed (bucketed)"]}
+long_cases = {} if ONLY_CHANGED else {"coop strips + chunks": (datasets._ragged(np.array([9000, 4097, 30]), alpha, rng, False), datasets._ragged(np.array([9500, 5000, 40000]), alpha, rng, False))}
 for name, (a, b) in long_cases.items():
     check(name, lev.compute_pairs(scope, a, b), orc.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, orc.RAPIDFUZZ_CLASS, threads=4))
 for name, (a, b) in cases.items():
@@ -42,6 +45,17 @@ for name, (a, b) in cases.items():
 u8 = sw.LevenshteinDistancesUtf8(scope)
 a, b = datasets.utf8_line_pairs(200, 10, 300)
 check("utf8 engine", u8.compute_pairs(scope, a, b), orc.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, orc.UTF8, threads=4))
+# second rename tier (more than 127 distinct multi-byte symbols in one pair), strings longer than one 512-byte round, bytes that are not UTF-8
+from stringwars_b200.tape import BytesTape
+_rng = np.random.default_rng(5)
+_mid = "".join(chr(0x4E00 + i) for i in range(200))
+_junk = [bytes(_rng.choice([0x41, 0x00, 0x7F, 0x80, 0xBF, 0xC3, 0xE4, 0xF0, 0xFF, 0x20], size=int(_rng.integers(0, 900))).astype(np.uint8)) for _ in range(40)]
+a = BytesTape.from_strings([_mid.encode(), ("жук naïve 日本語 " * 90).encode()] + _junk[:20])
+b = BytesTape.from_strings([(_mid[::-1] + "ж").encode(), ("naïve жук 日本 " * 80).encode()] + _junk[20:])
+check("utf8 engine (second tier, long, lenient)", u8.compute_pairs(scope, a, b), orc.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, orc.UTF8, threads=4))
+if ONLY_CHANGED:
+    print("ALL OK" if ok else "FAILED")
+    sys.exit(0 if ok else 1)
 btc, costs = sw.unary_class_costs(2, -1)
 a, b = datasets.acgt_pairs(30, 700)
 for cls, local in ((sw.NeedlemanWunschScores, False), (sw.SmithWatermanScores, True)):

@@ -104,7 +104,8 @@ static Plan make_plan(ScheduleStats &st) {
     for (int c = 0; c < SCHED_MCLASSES; ++c) {
         uint64_t class_count = 0;
         const uint64_t class_begin = running;
-        for (int b = 0; b < SCHED_NBINS; ++b) {
+        // longest texts first: the blocks that take longest start first and the class's tail is made of short ones
+        for (int b = SCHED_NBINS - 1; b >= 0; --b) {
             const int key = c * SCHED_NBINS + b;
             st.cursor[key] = (uint32_t)running;
             running += st.counts[key];
