@@ -350,6 +350,23 @@ def run_gates(bench, sw, datasets, scope, engine, args, peak, host_threads):
             row["kernel"] = engine.last_kernel
             entry[side_name] = row
         harness[name] = entry
+    # the code-point engine in the same shape: words in alphabetic scripts (63 distinct two-byte code points), cells in code points
+    utf8_x = sw.LevenshteinDistancesUtf8(scope)
+    entry = {}
+    for side_name, side in sides.items():
+        words = datasets.alphabetic_words(2 * side, seed=14)
+        q, c = words.subview(0, side), words.subview(side, 2 * side)
+        cp = np.add.reduceat(((words.data & 0xC0) != 0x80).astype(np.int64), words.offsets[:-1].astype(np.int64)).astype(np.float64)
+        tq, tc = sw.BytesTape.from_arrays(q.data[int(q.offsets[0]): int(q.offsets[-1])], q.offsets - q.offsets[0], memory="managed"), \
+            sw.BytesTape.from_arrays(c.data[int(c.offsets[0]): int(c.offsets[-1])], c.offsets - c.offsets[0], memory="managed")
+        m = sw.unified_mat(side, side, np.uint64, memory="managed")
+        ms, calls = bench.per_call_ms(lambda: utf8_x.compute_into(scope, tq, tc, m), budget_s=0.25)
+        row = {"side": side, "managed": {"gcups": float(np.outer(cp[:side], cp[side:]).sum()) / (ms * 1e-3) / 1e9, "ms_per_call": ms, "calls": calls}, "kernel": utf8_x.last_kernel}
+        if side <= 400:
+            ref = orc.levenshtein_cross(q.data, q.offsets, c.data, c.offsets, orc.UTF8, threads=host_threads)
+            row["managed"]["parity_ok"] = bool(np.array_equal(np.asarray(m).astype(np.uint64), ref))
+        entry[side_name] = row
+    harness["utf8_alphabetic_words"] = entry
     gates["harness_shape"] = harness
 
     # ---- the compiled twin of the reference's bench.rs block (harness/bench_similarities.cpp): the same call from C++, without

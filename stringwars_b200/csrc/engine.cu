@@ -90,10 +90,11 @@ static void destroy_ctx(DeviceCtx &c) {
     if (c.h_stats) cudaFreeHost(c.h_stats);
     if (c.d_spec) cudaFree(c.d_spec);
     if (c.h_spec) cudaFreeHost(c.h_spec);
+    if (c.h_words) cudaFreeHost(c.h_words);
     if (c.ev_offsets) cudaEventDestroy(c.ev_offsets);
     for (auto e : c.ev_chunks) cudaEventDestroy(e);
     for (DeviceBuffer *b : {&c.order, &c.a_data, &c.a_offs, &c.b_data, &c.b_offs, &c.out, &c.sym_a, &c.sym_a_offs, &c.sym_b, &c.sym_b_offs,
-                            &c.scan_tmp, &c.flags, &c.hscratch, &c.ren_a, &c.ren_a_offs, &c.ren_b, &c.ren_b_offs, &c.rx_a, &c.rx_b, &c.rx_a_offs, &c.rx_b_offs, &c.rx_out})
+                            &c.scan_tmp, &c.flags, &c.hscratch, &c.ren_a, &c.ren_a_offs, &c.ren_b, &c.ren_b_offs, &c.batch_dict, &c.rx_a, &c.rx_b, &c.rx_a_offs, &c.rx_b_offs, &c.rx_out})
         b->release();
 }
 
@@ -179,6 +180,7 @@ extern "C" swb_status_t swb_scope_create_devices(const int *devices, int num_dev
             e = cudaMemcpy(c.d_spec, &armed, sizeof(armed), cudaMemcpyHostToDevice);
         }
         if (e == cudaSuccess) e = cudaHostAlloc(&c.h_spec, sizeof(SpecPublished), cudaHostAllocMapped);
+        if (e == cudaSuccess) e = cudaHostAlloc(&c.h_words, 8 * sizeof(uint64_t), cudaHostAllocDefault);
         if (e == cudaSuccess) {
             memset(c.h_spec, 0, sizeof(SpecPublished));
             e = cudaHostGetDevicePointer((void **)&c.h_spec_dev, c.h_spec, 0);

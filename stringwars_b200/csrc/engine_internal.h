@@ -95,6 +95,7 @@ struct DeviceCtx {
     SpecReport *d_spec = nullptr;         // device: counters of a self-validating speculative launch
     SpecPublished *h_spec = nullptr;      // pinned + mapped: what its last block publishes
     SpecPublished *h_spec_dev = nullptr;  // device alias of h_spec
+    uint64_t *h_words = nullptr;          // pinned: 8 words for small synchronous readbacks (UTF-8 survey header, tape spans)
     uint32_t spec_seq = 0;
     cudaStream_t stats_stream = nullptr;  // stream that launch ran on (polled for errors while waiting)
     cudaEvent_t ev_offsets = nullptr;
@@ -102,6 +103,7 @@ struct DeviceCtx {
     DeviceBuffer order, a_data, a_offs, b_data, b_offs, out;
     DeviceBuffer sym_a, sym_a_offs, sym_b, sym_b_offs, scan_tmp, flags; // UTF-8 engine scratch
     DeviceBuffer ren_a, ren_a_offs, ren_b, ren_b_offs;                   // UTF-8 engine: pairs renamed to byte alphabets
+    DeviceBuffer batch_dict;                                             // UTF-8 engine: the batch-wide dictionary of a cross product
     DeviceBuffer hscratch; // per-column delta bits / boundary rows between row strips of the long-string kernels
     // multi_gpu.cu: receive buffers of a scattered shard, streams / events of the NCCL exchange
     DeviceBuffer rx_a, rx_b, rx_a_offs, rx_b_offs, rx_out;
@@ -200,6 +202,7 @@ static inline uint32_t round16(uint32_t x) { return (x + 15u) & ~15u; }
 // `completed` (optional) is set when the call has already SEEN the batch finish (a self-validating launch whose report
 // arrived): results are written and visible device-wide, no stream synchronisation is needed to know it.
 swb_status_t run_device_batch(swb_engine *eng, int dev_index, PairSpace ps, cudaStream_t stream, const char **err, bool *completed = nullptr);
+constexpr uint64_t SPAN_UNKNOWN = ~0ull; // run_device_batch_utf8: the caller cannot see the offsets (device / managed memory); the engine reads them
 // Same for the code-point engine (decodes both tapes first). n_a / n_b: strings per tape; *_bytes: their byte spans.
 swb_status_t run_device_batch_utf8(swb_engine *eng, int dev_index, PairSpace ps, uint64_t n_a, uint64_t n_b, uint64_t a_bytes,
                                    uint64_t b_bytes, cudaStream_t stream, const char **err);

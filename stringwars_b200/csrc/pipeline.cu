@@ -361,7 +361,24 @@ static swb_status_t pack_symbols(DeviceCtx &ctx, const uint8_t *data, const void
     return SWB_OK;
 }
 
-// Codepoint-level batch. n_a / n_b are the string counts of the two tapes, a_bytes / b_bytes their byte spans.
+// Total bytes spanned by the strings of two DEVICE-readable offsets arrays (one small synchronous readback for both).
+static swb_status_t device_spans(const void *a_offs, uint32_t a_width, uint64_t n_a, uint64_t *a_bytes, const void *b_offs, uint32_t b_width, uint64_t n_b,
+                                 uint64_t *b_bytes, cudaStream_t stream, const char **err) {
+    uint64_t ends[4] = {0, 0, 0, 0}; // little-endian: a u32 lands in the low half of the zeroed u64
+    SWB_CUDA(cudaMemcpyAsync(&ends[0], a_offs, a_width, cudaMemcpyDeviceToHost, stream));
+    SWB_CUDA(cudaMemcpyAsync(&ends[1], (const uint8_t *)a_offs + n_a * a_width, a_width, cudaMemcpyDeviceToHost, stream));
+    SWB_CUDA(cudaMemcpyAsync(&ends[2], b_offs, b_width, cudaMemcpyDeviceToHost, stream));
+    SWB_CUDA(cudaMemcpyAsync(&ends[3], (const uint8_t *)b_offs + n_b * b_width, b_width, cudaMemcpyDeviceToHost, stream));
+    SWB_CUDA(cudaStreamSynchronize(stream));
+    if (ends[1] < ends[0] || ends[3] < ends[2])
+        return fail(err, SWB_INVALID_ARG, "offsets are not monotonic (last %llu < first %llu)", (unsigned long long)(ends[1] < ends[0] ? ends[1] : ends[3]),
+                    (unsigned long long)(ends[1] < ends[0] ? ends[0] : ends[2]));
+    *a_bytes = ends[1] - ends[0], *b_bytes = ends[3] - ends[2];
+    return SWB_OK;
+}
+
+// Codepoint-level batch. n_a / n_b are the string counts of the two tapes, a_bytes / b_bytes their byte spans, or
+// SPAN_UNKNOWN when the caller cannot read the offsets (the engine then reads them where it synchronises anyway).
 swb_status_t swb::run_device_batch_utf8(swb_engine *eng, int dev_index, PairSpace ps, uint64_t n_a, uint64_t n_b,
                                         uint64_t a_bytes, uint64_t b_bytes, cudaStream_t stream, const char **err) {
     DeviceCtx &ctx = eng->scope->devs[dev_index];
@@ -371,6 +388,10 @@ swb_status_t swb::run_device_batch_utf8(swb_engine *eng, int dev_index, PairSpac
     const uint32_t a32 = ps.offs32 & 1u, b32 = (ps.offs32 >> 1) & 1u;
     // Element-wise pairs: ONE pass renames every pair to a byte alphabet (utf8_rename_kernel; pure-ASCII text goes through
     // it like any other) and the byte kernels do the rest.
+    const bool try_dict = ps.n_c != 0 && eng->algorithm != SWB_ALGO_WAVEFRONT;
+    if (!try_dict && (a_bytes == SPAN_UNKNOWN || b_bytes == SPAN_UNKNOWN) &&
+        (st = device_spans(ps.a_offs, a32 ? 4 : 8, n_a, &a_bytes, ps.b_offs, b32 ? 4 : 8, n_b, &b_bytes, stream, err)) != SWB_OK)
+        return st;
     if (ps.n_c == 0 && eng->algorithm != SWB_ALGO_WAVEFRONT) {
         SWB_CUDA(ctx.ren_a.reserve(a_bytes + 64));
         SWB_CUDA(ctx.ren_b.reserve(b_bytes + 64));
@@ -399,19 +420,68 @@ swb_status_t swb::run_device_batch_utf8(swb_engine *eng, int dev_index, PairSpac
             }
         }
     }
-    // Cross products, pairs with too many distinct symbols, the explicit wavefront algorithm: 32-bit symbols
-    // (count -> scan -> pack), pure-ASCII batches excepted (bytes ARE code points: the byte kernels as they are).
-    SWB_CUDA(cudaMemsetAsync(d_flag, 0x01, sizeof(uint32_t), stream));
-    if ((st = count_symbols(ctx, ps.a_data, ps.a_offs, a32, n_a, ctx.sym_a_offs, d_flag, stream, err)) != SWB_OK) return st;
+    // Cross products: a survey pass counts symbols, looks for non-ASCII bytes and numbers the batch's multi-byte symbols in
+    // one batch-wide dictionary. Pure ASCII: bytes ARE code points, the byte kernels as they are. At most 127 distinct
+    // multi-byte symbols: both tapes are translated to byte tapes (count -> scan -> translate) and the byte cross-product
+    // kernels do the rest. Anything wider, pairs with too many distinct symbols and the explicit wavefront algorithm:
+    // 32-bit symbols (count -> scan -> pack) on the wavefront kernel.
     const bool same_tape = ps.a_data == ps.b_data && ps.a_offs == ps.b_offs && n_a == n_b && a32 == b32;
-    if (!same_tape && (st = count_symbols(ctx, ps.b_data, ps.b_offs, b32, n_b, ctx.sym_b_offs, d_flag, stream, err)) != SWB_OK) return st;
-    const uint64_t *a_so = (const uint64_t *)ctx.sym_a_offs.ptr, *b_so = same_tape ? a_so : (const uint64_t *)ctx.sym_b_offs.ptr;
-    uint32_t h_ascii = 0;
-    SWB_CUDA(cudaMemcpyAsync(&h_ascii, d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    SWB_CUDA(cudaStreamSynchronize(stream));
+    const uint64_t *a_so = nullptr, *b_so = nullptr;
+    uint32_t h_ascii = 0, h_distinct = 0xFFFFFFFFu;
+    const TapeArg ta{ps.a_data, ps.a_offs, a32, n_a}, tb{ps.b_data, ps.b_offs, b32, same_tape ? 0 : n_b};
+    if (try_dict) {
+        SWB_CUDA(ctx.batch_dict.reserve(sizeof(BatchDict)));
+        SWB_CUDA(ctx.sym_a_offs.reserve((n_a + 1) * sizeof(uint64_t)));
+        SWB_CUDA(ctx.sym_b_offs.reserve((n_b + 1) * sizeof(uint64_t)));
+        BatchDict *dict = (BatchDict *)ctx.batch_dict.ptr;
+        SWB_CUDA(cudaMemsetAsync(dict, 0xFF, sizeof(BatchDict), stream));
+        utf8_survey_kernel<<<(unsigned)(((ta.n + tb.n) * 32 + 255) / 256), 256, 0, stream>>>(ta, (uint64_t *)ctx.sym_a_offs.ptr, tb, (uint64_t *)ctx.sym_b_offs.ptr, dict);
+        g_launches++;
+        SWB_CUDA(cudaGetLastError());
+        SWB_CUDA(cudaMemcpyAsync(ctx.h_words, dict, offsetof(BatchDict, keys), cudaMemcpyDeviceToHost, stream)); // {ascii, distinct - 1, -, spans}
+        SWB_CUDA(cudaStreamSynchronize(stream));
+        const uint32_t *head = reinterpret_cast<const uint32_t *>(ctx.h_words);
+        h_ascii = head[0], h_distinct = head[1] + 1u;
+        const uint64_t *span = ctx.h_words + 2;
+        if (span[1] < span[0] || (!same_tape && span[3] < span[2])) return fail(err, SWB_INVALID_ARG, "offsets are not monotonic (last offset before the first)");
+        if (a_bytes == SPAN_UNKNOWN) a_bytes = span[1] - span[0];
+        if (b_bytes == SPAN_UNKNOWN) b_bytes = same_tape ? a_bytes : span[3] - span[2];
+    } else {
+        SWB_CUDA(cudaMemsetAsync(d_flag, 0x01, sizeof(uint32_t), stream));
+        if ((st = count_symbols(ctx, ps.a_data, ps.a_offs, a32, n_a, ctx.sym_a_offs, d_flag, stream, err)) != SWB_OK) return st;
+        if (!same_tape && (st = count_symbols(ctx, ps.b_data, ps.b_offs, b32, n_b, ctx.sym_b_offs, d_flag, stream, err)) != SWB_OK) return st;
+        SWB_CUDA(cudaMemcpyAsync(&h_ascii, d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        SWB_CUDA(cudaStreamSynchronize(stream));
+    }
+    a_so = (const uint64_t *)ctx.sym_a_offs.ptr, b_so = same_tape ? a_so : (const uint64_t *)ctx.sym_b_offs.ptr;
     if (h_ascii != 0) return run_device_batch(eng, dev_index, ps, stream, err);
-    if ((st = scan_symbols(ctx, n_a, ctx.sym_a_offs, stream, err)) != SWB_OK) return st;
-    if (!same_tape && (st = scan_symbols(ctx, n_b, ctx.sym_b_offs, stream, err)) != SWB_OK) return st;
+    if (std::max(n_a, n_b) < (1u << 16)) { // a few thousand strings: one block per tape
+        utf8_small_scan_kernel<<<same_tape ? 1 : 2, SMALL_SCAN_THREADS, 0, stream>>>((uint64_t *)ctx.sym_a_offs.ptr, n_a + 1, (uint64_t *)ctx.sym_b_offs.ptr, n_b + 1);
+        g_launches++;
+        SWB_CUDA(cudaGetLastError());
+    } else {
+        if ((st = scan_symbols(ctx, n_a, ctx.sym_a_offs, stream, err)) != SWB_OK) return st;
+        if (!same_tape && (st = scan_symbols(ctx, n_b, ctx.sym_b_offs, stream, err)) != SWB_OK) return st;
+    }
+    if (try_dict && h_distinct <= BATCH_DICT_CAP) {
+        SWB_CUDA(ctx.ren_a.reserve(a_bytes + 64));
+        SWB_CUDA(ctx.ren_a_offs.reserve((n_a + 1) * sizeof(uint64_t)));
+        if (!same_tape) {
+            SWB_CUDA(ctx.ren_b.reserve(b_bytes + 64));
+            SWB_CUDA(ctx.ren_b_offs.reserve((n_b + 1) * sizeof(uint64_t)));
+        }
+        utf8_translate_kernel<<<(unsigned)(((ta.n + tb.n) * 32 + 255) / 256), 256, 0, stream>>>(ta, a_so, (uint8_t *)ctx.ren_a.ptr, (uint64_t *)ctx.ren_a_offs.ptr, tb, b_so,
+                                                                                              (uint8_t *)ctx.ren_b.ptr, (uint64_t *)ctx.ren_b_offs.ptr,
+                                                                                              (const BatchDict *)ctx.batch_dict.ptr);
+        g_launches++;
+        SWB_CUDA(cudaGetLastError());
+        PairSpace ren = ps;
+        ren.a_data = (const uint8_t *)ctx.ren_a.ptr, ren.a_offs = (const uint64_t *)ctx.ren_a_offs.ptr;
+        ren.b_data = same_tape ? ren.a_data : (const uint8_t *)ctx.ren_b.ptr;
+        ren.b_offs = same_tape ? ren.a_offs : (const uint64_t *)ctx.ren_b_offs.ptr;
+        ren.len_shift = 0, ren.offs32 = 0;
+        return run_device_batch(eng, dev_index, ren, stream, err);
+    }
     if ((st = pack_symbols(ctx, ps.a_data, ps.a_offs, a32, n_a, a_bytes, ctx.sym_a, ctx.sym_a_offs, stream, err)) != SWB_OK) return st;
     if (!same_tape && (st = pack_symbols(ctx, ps.b_data, ps.b_offs, b32, n_b, b_bytes, ctx.sym_b, ctx.sym_b_offs, stream, err)) != SWB_OK) return st;
     PairSpace sym = ps;
@@ -420,32 +490,6 @@ swb_status_t swb::run_device_batch_utf8(swb_engine *eng, int dev_index, PairSpac
     sym.b_offs = b_so;
     sym.len_shift = 2, sym.offs32 = 0;
     return run_device_batch(eng, dev_index, sym, stream, err);
-}
-
-// Total bytes spanned by n strings of a DEVICE-readable offsets array (one small synchronous readback).
-static swb_status_t device_span(const void *offs, uint32_t width, uint64_t n, cudaStream_t stream, uint64_t *bytes, const char **err) {
-    uint64_t ends[2] = {0, 0};
-    SWB_CUDA(cudaMemcpyAsync(&ends[0], offs, width, cudaMemcpyDeviceToHost, stream));
-    SWB_CUDA(cudaMemcpyAsync(&ends[1], (const uint8_t *)offs + n * width, width, cudaMemcpyDeviceToHost, stream));
-    SWB_CUDA(cudaStreamSynchronize(stream));
-    if (ends[1] < ends[0]) return fail(err, SWB_INVALID_ARG, "offsets are not monotonic (last %llu < first %llu)", (unsigned long long)ends[1], (unsigned long long)ends[0]);
-    *bytes = ends[1] - ends[0];
-    return SWB_OK;
-}
-// Total bytes spanned by the strings of two DEVICE-readable offsets arrays (one small synchronous readback for both).
-static swb_status_t device_spans(const void *a_offs, uint32_t a_width, uint64_t n_a, uint64_t *a_bytes, const void *b_offs, uint32_t b_width, uint64_t n_b,
-                                 uint64_t *b_bytes, cudaStream_t stream, const char **err) {
-    uint64_t ends[4] = {0, 0, 0, 0}; // little-endian: a u32 lands in the low half of the zeroed u64
-    SWB_CUDA(cudaMemcpyAsync(&ends[0], a_offs, a_width, cudaMemcpyDeviceToHost, stream));
-    SWB_CUDA(cudaMemcpyAsync(&ends[1], (const uint8_t *)a_offs + n_a * a_width, a_width, cudaMemcpyDeviceToHost, stream));
-    SWB_CUDA(cudaMemcpyAsync(&ends[2], b_offs, b_width, cudaMemcpyDeviceToHost, stream));
-    SWB_CUDA(cudaMemcpyAsync(&ends[3], (const uint8_t *)b_offs + n_b * b_width, b_width, cudaMemcpyDeviceToHost, stream));
-    SWB_CUDA(cudaStreamSynchronize(stream));
-    if (ends[1] < ends[0] || ends[3] < ends[2])
-        return fail(err, SWB_INVALID_ARG, "offsets are not monotonic (last %llu < first %llu)", (unsigned long long)(ends[1] < ends[0] ? ends[1] : ends[3]),
-                    (unsigned long long)(ends[1] < ends[0] ? ends[0] : ends[2]));
-    *a_bytes = ends[1] - ends[0], *b_bytes = ends[3] - ends[2];
-    return SWB_OK;
 }
 
 // ------------------------------------------------------------------------------------------ device-resident API
@@ -468,9 +512,7 @@ extern "C" swb_status_t swb_compute_pairs_device(swb_engine_t *engine, int devic
     SWB_CUDA(cudaSetDevice(engine->scope->devs[device_index].device));
     PairSpace ps = make_pair_space(a_data, a_offsets, b_data, b_offsets, n_pairs, 0, 0, out, 0, 0);
     if (engine->kind == ENGINE_LEVENSHTEIN_UTF8) {
-        uint64_t a_bytes = 0, b_bytes = 0;
-        if ((st = device_spans(a_offsets, 8, n_pairs, &a_bytes, b_offsets, 8, n_pairs, &b_bytes, (cudaStream_t)cuda_stream, err)) != SWB_OK) return st;
-        return run_device_batch_utf8(engine, device_index, ps, n_pairs, n_pairs, a_bytes, b_bytes, (cudaStream_t)cuda_stream, err);
+        return run_device_batch_utf8(engine, device_index, ps, n_pairs, n_pairs, SPAN_UNKNOWN, SPAN_UNKNOWN, (cudaStream_t)cuda_stream, err);
     }
     return run_device_batch(engine, device_index, ps, (cudaStream_t)cuda_stream, err);
 }
@@ -489,9 +531,7 @@ extern "C" swb_status_t swb_compute_pairs_device_view(swb_engine_t *engine, int 
     const uint32_t offs32 = (a->offset_bits == 32 ? 1u : 0u) | (b->offset_bits == 32 ? 2u : 0u);
     PairSpace ps = make_pair_space(a->data, a->offsets, b->data, b->offsets, a->n, 0, 0, out, (uint32_t)out_type, offs32);
     if (engine->kind == ENGINE_LEVENSHTEIN_UTF8) {
-        uint64_t a_bytes = 0, b_bytes = 0;
-        if ((st = device_spans(a->offsets, a->offset_bits / 8, a->n, &a_bytes, b->offsets, b->offset_bits / 8, b->n, &b_bytes, (cudaStream_t)cuda_stream, err)) != SWB_OK) return st;
-        return run_device_batch_utf8(engine, device_index, ps, a->n, b->n, a_bytes, b_bytes, (cudaStream_t)cuda_stream, err);
+        return run_device_batch_utf8(engine, device_index, ps, a->n, b->n, SPAN_UNKNOWN, SPAN_UNKNOWN, (cudaStream_t)cuda_stream, err);
     }
     return run_device_batch(engine, device_index, ps, (cudaStream_t)cuda_stream, err);
 }
@@ -508,9 +548,7 @@ extern "C" swb_status_t swb_compute_cross_device(swb_engine_t *engine, int devic
     SWB_CUDA(cudaSetDevice(engine->scope->devs[device_index].device));
     PairSpace ps = make_pair_space(q_data, q_offsets, c_data, c_offsets, (uint64_t)n_queries * n_candidates, n_candidates, row_stride, out, 0, 0);
     if (engine->kind == ENGINE_LEVENSHTEIN_UTF8) {
-        uint64_t a_bytes = 0, b_bytes = 0;
-        if ((st = device_spans(q_offsets, 8, n_queries, &a_bytes, c_offsets, 8, n_candidates, &b_bytes, (cudaStream_t)cuda_stream, err)) != SWB_OK) return st;
-        return run_device_batch_utf8(engine, device_index, ps, n_queries, n_candidates, a_bytes, b_bytes, (cudaStream_t)cuda_stream, err);
+        return run_device_batch_utf8(engine, device_index, ps, n_queries, n_candidates, SPAN_UNKNOWN, SPAN_UNKNOWN, (cudaStream_t)cuda_stream, err);
     }
     return run_device_batch(engine, device_index, ps, (cudaStream_t)cuda_stream, err);
 }
@@ -905,8 +943,8 @@ static swb_status_t host_cross(swb_engine *engine, const Side &Q, const Side &C,
         if (trace_enabled()) t_placed = now_ms();
         if (engine->kind == ENGINE_LEVENSHTEIN_UTF8) {
             uint64_t q_bytes = q.hi_off - q.lo_off, c_bytes = c.hi_off - c.lo_off;
-            if (!Q.host_offsets() && (st = device_span(q.offs_at_lo, Q.width, q_hi - q_lo, ctx.compute_stream, &q_bytes, err)) != SWB_OK) return st;
-            if (!C.host_offsets() && (st = device_span(c.offs_at_lo, C.width, n_c, ctx.compute_stream, &c_bytes, err)) != SWB_OK) return st;
+            if (!Q.host_offsets()) q_bytes = SPAN_UNKNOWN;
+            if (!C.host_offsets()) c_bytes = SPAN_UNKNOWN;
             if ((st = run_device_batch_utf8(engine, d, ps, q_hi - q_lo, n_c, q_bytes, c_bytes, ctx.compute_stream, err)) != SWB_OK) return drain(scope), st;
         } else if ((st = run_device_batch(engine, d, ps, ctx.compute_stream, err, &seen_done[d])) != SWB_OK) {
             return drain(scope), st;

@@ -82,6 +82,174 @@ __global__ void __launch_bounds__(256) utf8_pack_kernel(const uint8_t *data, con
     }
 }
 
+// ---- Batch-wide alphabet compaction for cross products. Every query meets every candidate, so the dictionary is one per
+// BATCH, in global memory: plain ASCII keeps its value, every other symbol of either tape is numbered 129, 130, ... as the
+// survey pass (which also counts symbols and looks for non-ASCII bytes, like utf8_count_kernel) first meets it. A batch with
+// at most 127 distinct multi-byte symbols — text in one or two alphabetic scripts — is then translated to byte tapes with
+// ordinary n + 1 offsets and runs on the byte cross-product kernels; anything wider keeps the 32-bit wavefront path.
+// The harness calls with a few hundred to a few thousand short strings per side, so this path is about launches, not
+// bytes: one memset (every field starts as 0xFF..), one survey, one scan and one translate launch for BOTH tapes.
+constexpr uint32_t BATCH_DICT_SLOTS = 1024, BATCH_DICT_CAP = 127, BATCH_DICT_BASE = 128;
+constexpr uint32_t RENAME_EMPTY_KEY = 0xFFFFFFFFu; // no packed symbol: a lead byte followed by continuation bytes (at most 0xBF)
+struct BatchDict {
+    uint32_t ascii;                  // stays 0xFFFFFFFF while no byte >= 0x80 has been seen
+    uint32_t distinct_minus_1;       // symbols numbered so far, minus one (starts at 0xFFFFFFFF); above BATCH_DICT_CAP the batch does not fit
+    uint32_t pad[2];
+    uint64_t span[4];                // first and last offset of tape A, of tape B (written by the survey: the host sizes its buffers from them)
+    uint32_t keys[BATCH_DICT_SLOTS]; // packed symbols, RENAME_EMPTY_KEY where free
+    uint8_t ids[BATCH_DICT_SLOTS];
+};
+// One byte tape as the kernels below see it.
+struct TapeArg {
+    const uint8_t *data;
+    const void *offs;
+    uint32_t offs32;
+    uint64_t n;
+};
+
+__device__ __forceinline__ void batch_dict_insert(BatchDict *d, uint32_t key) {
+    if (*reinterpret_cast<volatile uint32_t *>(&d->distinct_minus_1) + 1u > BATCH_DICT_CAP) return; // already too wide: the host falls back
+    uint32_t h = (key * 0x9E3779B1u) >> 22;
+    for (uint32_t probes = 0; probes < BATCH_DICT_SLOTS; ++probes, h = (h + 1u) & (BATCH_DICT_SLOTS - 1u)) {
+        uint32_t at = reinterpret_cast<volatile uint32_t *>(d->keys)[h];
+        if (at == RENAME_EMPTY_KEY) {
+            at = atomicCAS(&d->keys[h], RENAME_EMPTY_KEY, key);
+            if (at == RENAME_EMPTY_KEY) {
+                const uint32_t number = atomicAdd(&d->distinct_minus_1, 1u) + 2u;
+                d->ids[h] = (uint8_t)min(BATCH_DICT_BASE + number, 255u);
+                return;
+            }
+        }
+        if (at == key) return;
+    }
+    atomicAdd(&d->distinct_minus_1, BATCH_DICT_SLOTS); // table full: reads as "too wide"
+}
+__device__ __forceinline__ uint32_t batch_dict_lookup(const BatchDict *d, uint32_t key) {
+    uint32_t h = (key * 0x9E3779B1u) >> 22;
+    for (uint32_t probes = 0; probes < BATCH_DICT_SLOTS; ++probes, h = (h + 1u) & (BATCH_DICT_SLOTS - 1u)) {
+        const uint32_t at = __ldg(&d->keys[h]);
+        if (at == key) return __ldg(&d->ids[h]);
+        if (at == RENAME_EMPTY_KEY) break;
+    }
+    return BATCH_DICT_BASE; // not reachable after a survey of the same tape
+}
+
+// The symbol that starts at byte p of a string (p is a lead byte): lead byte and up to three continuation bytes, big-endian.
+__device__ __forceinline__ uint32_t symbol_at(const uint8_t *s, uint32_t p, uint32_t len, uint32_t lead_byte) {
+    uint32_t sym = lead_byte;
+    for (uint32_t k = 1; k < 4 && p + k < len; ++k) {
+        const uint32_t c = ldg1(s + p + k);
+        if ((c & 0xC0u) != 0x80u) break;
+        sym = (sym << 8) | c;
+    }
+    return sym;
+}
+
+// One warp per string of either tape, a byte per lane: counts[i + 1] = 4 * symbols of string i (the unit of the 32-bit
+// fallback path), the ASCII flag is cleared when a byte >= 0x80 is seen, every symbol that is not a plain ASCII byte enters
+// the dictionary.
+__global__ void __launch_bounds__(256) utf8_survey_kernel(TapeArg ta, uint64_t *a_counts, TapeArg tb, uint64_t *b_counts, BatchDict *dict) {
+    uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= ta.n + tb.n) return;
+    const bool second = warp >= ta.n;
+    const TapeArg &t = second ? tb : ta;
+    uint64_t *counts = second ? b_counts : a_counts;
+    if (second) warp -= ta.n;
+    const uint64_t o0 = tape_offset(t.offs, t.offs32, warp), o1 = tape_offset(t.offs, t.offs32, warp + 1);
+    if (warp == 0 && lane == 0) counts[0] = 0, dict->span[second ? 2 : 0] = o0;
+    if (warp + 1 == t.n && lane == 0) dict->span[second ? 3 : 1] = o1;
+    const uint8_t *s = t.data + o0;
+    const uint32_t len = o1 < o0 ? 0u : (uint32_t)(o1 - o0);
+    uint32_t count = 0;
+    bool high = false;
+    for (uint32_t base = 0; base < len; base += 32) {
+        const uint32_t p = base + lane;
+        const uint32_t b = p < len ? ldg1(s + p) : 0x80u;
+        const bool lead = p < len && (b & 0xC0u) != 0x80u;
+        high = high || (p < len && b >= 0x80u);
+        count += __popc(__ballot_sync(0xffffffffu, lead));
+        if (lead) {
+            const uint32_t sym = symbol_at(s, p, len, b);
+            if (sym >= 0x80u) batch_dict_insert(dict, sym);
+        }
+    }
+    if (__any_sync(0xffffffffu, high) && lane == 0) atomicAnd(&dict->ascii, 0u);
+    if (lane == 0) counts[warp + 1] = 4ull * count;
+}
+
+// Inclusive scan in place of one or two small arrays, one block each (a few thousand entries: not worth a device-wide scan).
+constexpr int SMALL_SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(SMALL_SCAN_THREADS) utf8_small_scan_kernel(uint64_t *a, uint64_t n_a, uint64_t *b, uint64_t n_b) {
+    uint64_t *v = blockIdx.x == 0 ? a : b;
+    const uint64_t n = blockIdx.x == 0 ? n_a : n_b;
+    __shared__ uint64_t warp_sums[32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint64_t base = 0; base < n; base += SMALL_SCAN_THREADS) {
+        const uint64_t i = base + threadIdx.x;
+        uint64_t x = i < n ? v[i] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t up = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += up;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t w = warp_sums[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint64_t up = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= d) w += up;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const uint64_t before = carry + (warp ? warp_sums[warp - 1] : 0);
+        if (i < n) v[i] = x + before;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warp_sums[31];
+        __syncthreads();
+    }
+}
+
+// One warp per string of either tape: the ids of string i at out + sym_offs[i] / 4, and the byte tape's offsets next to them.
+__global__ void __launch_bounds__(256) utf8_translate_kernel(TapeArg ta, const uint64_t *a_sym_offs, uint8_t *a_out, uint64_t *a_out_offs, TapeArg tb,
+                                                             const uint64_t *b_sym_offs, uint8_t *b_out, uint64_t *b_out_offs, const BatchDict *dict) {
+    uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= ta.n + tb.n) return;
+    const bool second = warp >= ta.n;
+    const TapeArg &t = second ? tb : ta;
+    const uint64_t *sym_offs = second ? b_sym_offs : a_sym_offs;
+    uint8_t *out = second ? b_out : a_out;
+    uint64_t *out_offs = second ? b_out_offs : a_out_offs;
+    if (second) warp -= ta.n;
+    const uint64_t o0 = tape_offset(t.offs, t.offs32, warp), o1 = tape_offset(t.offs, t.offs32, warp + 1);
+    const uint8_t *s = t.data + o0;
+    const uint32_t len = o1 < o0 ? 0u : (uint32_t)(o1 - o0);
+    uint8_t *dst = out + (sym_offs[warp] >> 2);
+    if (lane == 0) {
+        out_offs[warp] = sym_offs[warp] >> 2;
+        if (warp + 1 == t.n) out_offs[t.n] = sym_offs[t.n] >> 2;
+    }
+    uint32_t written = 0;
+    for (uint32_t base = 0; base < len; base += 32) {
+        const uint32_t p = base + lane;
+        const uint32_t b = p < len ? ldg1(s + p) : 0x80u;
+        const bool lead = p < len && (b & 0xC0u) != 0x80u;
+        const uint32_t mask = __ballot_sync(0xffffffffu, lead);
+        if (lead) {
+            const uint32_t sym = symbol_at(s, p, len, b);
+            dst[written + __popc(mask & ((1u << lane) - 1u))] = (uint8_t)(sym < 0x80u ? sym : batch_dict_lookup(dict, sym));
+        }
+        written += __popc(mask);
+    }
+}
+
 // Per-pair alphabet compaction for element-wise pairs. The bit-vector kernels index their match tables by BYTE, and an
 // edit distance only ever asks whether pattern symbol i equals text symbol j. So each pair's code points are renamed to
 // bytes and the renamed pair, which has exactly the distance of the original, runs on the byte kernels.

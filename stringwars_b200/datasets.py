@@ -85,6 +85,20 @@ def _vocabulary(rng: np.random.Generator, size: int = 50_000):
     return words
 
 
+def alphabetic_words(n: int, seed: int = SEED, memory: str = None) -> BytesTape:
+    """Words of 1..12 letters in alphabetic scripts — ASCII Latin, Latin-1 diacritics, Cyrillic (63 distinct two-byte code
+    points) — the shape of a one- or two-language leipzig1M word list: the code-point engine's cross product over them
+    fits one batch-wide byte alphabet."""
+    rng = np.random.default_rng(seed)
+    scripts = [[chr(c) for c in range(ord("a"), ord("z") + 1)],
+               [chr(c) for c in range(0xE0, 0xFF) if c != 0xF7] + [chr(c) for c in range(ord("a"), ord("z") + 1)],
+               [chr(c) for c in range(0x430, 0x450)]]
+    which = rng.choice(3, size=n, p=[0.4, 0.2, 0.4])
+    lens = rng.integers(1, 13, size=n)
+    words = ["".join(scripts[w][i] for i in rng.integers(0, len(scripts[w]), size=l)) for w, l in zip(which, lens)]
+    return BytesTape.from_strings(words, memory=memory)
+
+
 def utf8_line_pairs(n: int = 100_000, lo: int = 128, hi: int = 512, seed: int = SEED,
                     pinned: bool = False) -> Tuple[BytesTape, BytesTape]:
     """Config 3: valid-UTF-8 'lines' of byte length ~ U{lo..hi} cut at codepoint boundaries, built from

@@ -259,6 +259,35 @@ def test_utf8_engine_cross(scope, lev_utf8, oracle):
     assert np.array_equal(got, want)
 
 
+def test_utf8_engine_cross_batch_dictionary(scope, lev_utf8, oracle):
+    """Cross products whose multi-byte symbols fit one batch-wide byte alphabet (at most 127 distinct) are translated to
+    byte tapes and run the byte kernels; wider batches keep the 32-bit wavefront. Both bit-exact with the oracle."""
+    rng = np.random.default_rng(31)
+    words = datasets.alphabetic_words(700, seed=31)
+    q, c = words.subview(0, 300), words.subview(300, 700)
+    got = lev_utf8.compute(scope, q, c)
+    assert np.array_equal(got, oracle.levenshtein_cross(q.data, q.offsets, c.data, c.offsets, oracle.UTF8, threads=8))
+    assert "wavefront" not in lev_utf8.last_kernel, lev_utf8.last_kernel
+    assert (got != oracle.levenshtein_cross(q.data, q.offsets, c.data, c.offsets, threads=8)).any()  # not the byte distance by accident
+    # the tape against itself, longer strings (lines of words), empty strings, u32 offsets
+    lines = [" ".join(bytes(words[int(i)]).decode() for i in rng.integers(0, 700, size=int(rng.integers(0, 30)))) for _ in range(90)]
+    lines[5] = lines[40] = ""
+    tape = BytesTape.from_strings(lines, offset_dtype=np.uint32)
+    got = lev_utf8.compute(scope, tape, tape)
+    assert np.array_equal(got, oracle.levenshtein_cross(tape.data, tape.offsets, tape.data, tape.offsets, oracle.UTF8, threads=8))
+    assert "wavefront" not in lev_utf8.last_kernel, lev_utf8.last_kernel
+    # bytes that are not UTF-8: the oracle's lenient split, 58 distinct multi-byte "symbols"
+    junk = [bytes(rng.choice([0x41, 0x00, 0x80, 0xBF, 0xC3, 0xF0], size=int(rng.integers(0, 40))).astype(np.uint8)) for _ in range(160)]
+    jq, jc = BytesTape.from_strings(junk[:70]), BytesTape.from_strings(junk[70:])
+    got = lev_utf8.compute(scope, jq, jc)
+    assert np.array_equal(got, oracle.levenshtein_cross(jq.data, jq.offsets, jc.data, jc.offsets, oracle.UTF8, threads=8))
+    # one string with 200 distinct ideographs: too wide, the batch runs the wavefront kernel
+    wide = BytesTape.from_strings([bytes(words[i]) for i in range(60)] + ["".join(chr(0x4E00 + i) for i in range(200)).encode()])
+    got = lev_utf8.compute(scope, wide, q.subview(0, 50))
+    assert np.array_equal(got, oracle.levenshtein_cross(wide.data, wide.offsets, q.data, q.offsets[:51], oracle.UTF8, threads=8))
+    assert "wavefront" in lev_utf8.last_kernel, lev_utf8.last_kernel
+
+
 @pytest.mark.parametrize("algo", [sw.ALGO_AUTO, sw.ALGO_WAVEFRONT])
 def test_very_long_and_lopsided_pairs(scope, lev, oracle, algo):
     """Lane-group bit-vector kernels up to 4096 pattern bytes, wavefront row strips beyond, short-vs-long pairs."""
