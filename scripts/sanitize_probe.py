@@ -53,6 +53,13 @@ _junk = [bytes(_rng.choice([0x41, 0x00, 0x7F, 0x80, 0xBF, 0xC3, 0xE4, 0xF0, 0xFF
 a = BytesTape.from_strings([_mid.encode(), ("жук naïve 日本語 " * 90).encode()] + _junk[:20])
 b = BytesTape.from_strings([(_mid[::-1] + "ж").encode(), ("naïve жук 日本 " * 80).encode()] + _junk[20:])
 check("utf8 engine (second tier, long, lenient)", u8.compute_pairs(scope, a, b), orc.levenshtein_pairs(a.data, a.offsets, b.data, b.offsets, orc.UTF8, threads=4))
+# code-point cross products: batch-wide byte alphabet (survey -> scan -> translate -> byte cross kernels), same tape, too wide -> wavefront
+w = datasets.alphabetic_words(260, seed=3)
+q, c = w.subview(0, 100), w.subview(100, 260)
+check("utf8 cross (batch dictionary)", u8.compute(scope, q, c), orc.levenshtein_cross(q.data, q.offsets, c.data, c.offsets, orc.UTF8, threads=4))
+check("utf8 cross (same tape)", u8.compute(scope, q, q), orc.levenshtein_cross(q.data, q.offsets, q.data, q.offsets, orc.UTF8, threads=4))
+wide = BytesTape.from_strings([bytes(w[i]) for i in range(40)] + ["".join(chr(0x4E00 + i) for i in range(200)).encode()])
+check("utf8 cross (too wide: wavefront)", u8.compute(scope, wide, q), orc.levenshtein_cross(wide.data, wide.offsets, q.data, q.offsets, orc.UTF8, threads=4))
 if ONLY_CHANGED:
     print("ALL OK" if ok else "FAILED")
     sys.exit(0 if ok else 1)

@@ -530,3 +530,55 @@ def test_utf8_symbol_split_and_rename_model():
     assert _rename_model(wide[:128].encode(), wide.encode(), True) is None
     assert _rename_model((wide[:200] + "abc").encode(), wide.encode(), False) is not None
     assert _rename_model(wide[:256].encode(), wide.encode(), False) is None
+
+
+def test_utf8_batch_dictionary_model():
+    """utf8.cuh, cross products: one dictionary per batch. Plain ASCII keeps its value, every other symbol (big-endian packing
+    of a lead byte and up to three continuation bytes) is numbered from 129 in whatever order the survey meets it; the
+    translated byte tapes have the code-point distances of the originals for EVERY pair of the cross product, and a batch with
+    more than 127 distinct multi-byte symbols does not fit."""
+    from oracle import oracle
+
+    def symbols(data):  # symbol_at() over the lead bytes of a string
+        out, i = [], 0
+        while i < len(data):
+            if (data[i] & 0xC0) == 0x80:
+                i += 1
+                continue
+            sym, k = data[i], 1
+            while k < 4 and i + k < len(data) and (data[i + k] & 0xC0) == 0x80:
+                sym = (sym << 8) | data[i + k]
+                k += 1
+            out.append(sym)
+            i += 1
+        return out
+
+    def translate(strings, order_rng):
+        numbers = {}
+        seen = [s for x in strings for s in symbols(x) if s >= 0x80]
+        order_rng.shuffle(seen)  # atomics: any insertion order
+        for s in seen:
+            if s not in numbers:
+                numbers[s] = len(numbers) + 1
+        if len(numbers) > 127:
+            return None
+        return [bytes(s if s < 0x80 else 128 + numbers[s] for s in symbols(x)) for x in strings]
+
+    rng = random.Random(21)
+    pool = "abcxyz éèßøñ жукпривет"
+    nasty = [0x41, 0x00, 0x80, 0xBF, 0xC3, 0xF0]
+    for trial in range(6):
+        if trial % 2:
+            strings = ["".join(rng.choice(pool) for _ in range(rng.randrange(0, 14))).encode() for _ in range(16)]
+        else:
+            strings = [bytes(rng.choice(nasty) for _ in range(rng.randrange(0, 14))) for _ in range(16)]
+        ren = translate(strings, rng)
+        assert ren is not None
+        q, c = strings[:6], strings[6:]
+        want = oracle.levenshtein_cross(*_tape(q), *_tape(c), oracle.UTF8)
+        for i in range(6):
+            for j in range(10):
+                assert pyref.levenshtein(ren[i], ren[6 + j]) == want[i, j], (q[i], c[j])
+    wide = ["".join(chr(0x4E00 + i) for i in range(k, k + 16)).encode() for k in range(0, 128, 16)]
+    assert translate(wide[:7] + ["日本語".encode()], rng) is not None  # 112 + 3 distinct
+    assert translate(wide + ["x".encode()], rng) is None               # 128 distinct ideographs: one too many
