@@ -442,6 +442,7 @@ swb_status_t swb::run_device_batch_utf8(swb_engine *eng, int dev_index, PairSpac
         SWB_CUDA(cudaStreamSynchronize(stream));
         const uint32_t *head = reinterpret_cast<const uint32_t *>(ctx.h_words);
         h_ascii = head[0], h_distinct = head[1] + 1u;
+        if (head[2] == 0u) return fail(err, SWB_INVALID_ARG, "offsets are not monotonic (or leave the tape, or a string spans 4 GiB or more)");
         const uint64_t *span = ctx.h_words + 2;
         if (span[1] < span[0] || (!same_tape && span[3] < span[2])) return fail(err, SWB_INVALID_ARG, "offsets are not monotonic (last offset before the first)");
         if (a_bytes == SPAN_UNKNOWN) a_bytes = span[1] - span[0];

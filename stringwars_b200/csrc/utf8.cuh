@@ -90,11 +90,12 @@ __global__ void __launch_bounds__(256) utf8_pack_kernel(const uint8_t *data, con
 // The harness calls with a few hundred to a few thousand short strings per side, so this path is about launches, not
 // bytes: one memset (every field starts as 0xFF..), one survey, one scan and one translate launch for BOTH tapes.
 constexpr uint32_t BATCH_DICT_SLOTS = 1024, BATCH_DICT_CAP = 127, BATCH_DICT_BASE = 128;
-constexpr uint32_t RENAME_EMPTY_KEY = 0xFFFFFFFFu; // no packed symbol: a lead byte followed by continuation bytes (at most 0xBF)
+constexpr uint32_t RENAME_EMPTY_KEY = 0xFFFFFFFFu; // no packed symbol (either packing): a lead byte with continuation bytes (at most 0xBF) or zeros around it
 struct BatchDict {
     uint32_t ascii;                  // stays 0xFFFFFFFF while no byte >= 0x80 has been seen
     uint32_t distinct_minus_1;       // symbols numbered so far, minus one (starts at 0xFFFFFFFF); above BATCH_DICT_CAP the batch does not fit
-    uint32_t pad[2];
+    uint32_t offsets_ok;             // stays 0xFFFFFFFF while every string lies inside its tape's span and runs forwards
+    uint32_t pad;
     uint64_t span[4];                // first and last offset of tape A, of tape B (written by the survey: the host sizes its buffers from them)
     uint32_t keys[BATCH_DICT_SLOTS]; // packed symbols, RENAME_EMPTY_KEY where free
     uint8_t ids[BATCH_DICT_SLOTS];
@@ -159,8 +160,13 @@ __global__ void __launch_bounds__(256) utf8_survey_kernel(TapeArg ta, uint64_t *
     const uint64_t o0 = tape_offset(t.offs, t.offs32, warp), o1 = tape_offset(t.offs, t.offs32, warp + 1);
     if (warp == 0 && lane == 0) counts[0] = 0, dict->span[second ? 2 : 0] = o0;
     if (warp + 1 == t.n && lane == 0) dict->span[second ? 3 : 1] = o1;
+    // this pass reads the strings before anything has validated the offsets: a string that runs backwards, spans 4 GiB or
+    // leaves [first offset, last offset] of its tape is not read, and the host fails the call with SWB_INVALID_ARG
+    const uint64_t first = tape_offset(t.offs, t.offs32, 0), last = tape_offset(t.offs, t.offs32, t.n);
+    const bool ok = o0 >= first && o1 >= o0 && o1 <= last && ((o1 - o0) >> 32) == 0u;
+    if (!ok && lane == 0) atomicAnd(&dict->offsets_ok, 0u);
     const uint8_t *s = t.data + o0;
-    const uint32_t len = o1 < o0 ? 0u : (uint32_t)(o1 - o0);
+    const uint32_t len = ok ? (uint32_t)(o1 - o0) : 0u;
     uint32_t count = 0;
     bool high = false;
     for (uint32_t base = 0; base < len; base += 32) {
@@ -272,7 +278,6 @@ __global__ void __launch_bounds__(256) utf8_translate_kernel(TapeArg ta, const u
 // call fails with SWB_INVALID_ARG; the pair is renamed to two empty strings and nothing outside the span is read).
 constexpr int RENAME_WARPS = 4;
 constexpr uint32_t RENAME_TABLE = 512;         // dictionary slots: at most 255 are ever numbered, so probes are short
-constexpr uint32_t RENAME_EMPTY = 0xFFFFFFFFu; // no packed symbol: byte 0 is a lead, bytes 1..3 continuation bytes (never 0xFF) or absent (0)
 constexpr uint32_t RENAME_OVERFLOW = 1u, RENAME_BAD_OFFSETS = 2u;
 
 // bit k: byte k of the word is >= 0x80
@@ -308,7 +313,7 @@ __global__ void __launch_bounds__(32 * RENAME_WARPS)
     const uint32_t a_len = (uint32_t)(ab1 - ab0), b_len = (uint32_t)(bb1 - bb0); // bytes
 #pragma unroll
     for (uint32_t i = 0; i < RENAME_TABLE / 128; ++i)
-        reinterpret_cast<uint4 *>(sh.keys)[i * 32 + lane] = make_uint4(RENAME_EMPTY, RENAME_EMPTY, RENAME_EMPTY, RENAME_EMPTY);
+        reinterpret_cast<uint4 *>(sh.keys)[i * 32 + lane] = make_uint4(RENAME_EMPTY_KEY, RENAME_EMPTY_KEY, RENAME_EMPTY_KEY, RENAME_EMPTY_KEY);
     __syncwarp();
     bool failed = false;
     uint32_t n_ids = 0; // symbols numbered so far (the same in every lane)
@@ -390,9 +395,9 @@ __global__ void __launch_bounds__(32 * RENAME_WARPS)
 #pragma unroll 1
                     for (uint32_t probes = 0; probes < RENAME_TABLE; ++probes, h = (h + 1u) & (RENAME_TABLE - 1u)) {
                         uint32_t at = sh.keys[h];
-                        if (dict && at == RENAME_EMPTY) {
-                            at = atomicCAS(&sh.keys[h], RENAME_EMPTY, key);
-                            if (at == RENAME_EMPTY) {
+                        if (dict && at == RENAME_EMPTY_KEY) {
+                            at = atomicCAS(&sh.keys[h], RENAME_EMPTY_KEY, key);
+                            if (at == RENAME_EMPTY_KEY) {
                                 won = true;
                                 break;
                             }
@@ -401,7 +406,7 @@ __global__ void __launch_bounds__(32 * RENAME_WARPS)
                             found = true;
                             break;
                         }
-                        if (at == RENAME_EMPTY) break; // not in the dictionary
+                        if (at == RENAME_EMPTY_KEY) break; // not in the dictionary
                     }
                 }
                 if (dict) { // the step's newcomers take the next numbers, in lane order

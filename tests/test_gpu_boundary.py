@@ -344,6 +344,14 @@ def test_non_monotonic_offsets_are_refused_not_faulted(scope, lev):
     with pytest.raises(sw.Error) as e:
         utf8.compute_pairs(scope, broken, b)
     assert e.value.status_name == "INVALID_ARG"
+    # ... and so does its cross product (the survey pass): candidates 4900..5100 of the broken tape, offsets in device memory
+    matrix = torch.zeros((50, 200), dtype=torch.int64, device=dev)
+    with pytest.raises(sw.Error) as e:
+        utf8.compute_cross_device(bd.data_ptr(), bo.data_ptr(), 50, ad.data_ptr(), ao.data_ptr() + 4900 * 8, 200, matrix.data_ptr(), 200)
+    assert e.value.status_name == "INVALID_ARG"
+    utf8.compute_cross_device(bd.data_ptr(), bo.data_ptr(), 50, ad.data_ptr(), good.data_ptr() + 4900 * 8, 200, matrix.data_ptr(), 200)
+    torch.cuda.synchronize()
+    assert np.array_equal(matrix.cpu().numpy().astype(np.uint64), lev.compute(scope, b.subview(0, 50), a.subview(4900, 5100)))
     torch.cuda.synchronize()
     # and the engines still work afterwards
     assert lev.compute_pairs(scope, a.subview(0, 100), b.subview(0, 100)).shape == (100,)
