@@ -28,6 +28,19 @@ def test_utf8_lines_are_valid_utf8_in_range():
     assert multibyte > 100  # mixed scripts really are there
 
 
+def test_alphabetic_words_fit_one_byte_alphabet():
+    """The code-point cross-product workload: valid UTF-8 words whose multi-byte code points (Latin-1, Cyrillic) number at
+    most 127 over the whole tape — what the engine's batch-wide byte alphabet needs (utf8.cuh BATCH_DICT_CAP)."""
+    words = datasets.alphabetic_words(3000, seed=2)
+    text = [words[i].decode("utf-8") for i in range(len(words))]
+    assert all(1 <= len(w) <= 12 for w in text)
+    wide = {ch for w in text for ch in w if ord(ch) >= 0x80}
+    assert 40 < len(wide) <= 127
+    assert any(ord(ch) < 0x80 for w in text for ch in w)
+    again = datasets.alphabetic_words(3000, seed=2)
+    assert np.array_equal(words.data, again.data) and np.array_equal(words.offsets, again.offsets)
+
+
 def test_cells_accounting_matches_harness_definition():
     a = BytesTape.from_strings([b"abc", b"", b"xy"])
     b = BytesTape.from_strings([b"abcd", b"q", b""])
